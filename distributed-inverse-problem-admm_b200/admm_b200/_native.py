@@ -1,0 +1,117 @@
+"""ctypes binding of libadmm_b200.so (C ABI in include/admm_b200.h).
+
+There is no CPU fallback: if the shared library is missing it is built with nvcc for sm_100a; if a compute
+entry point is called without a CUDA device it raises.  PyTorch only supplies device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)                      # distributed-inverse-problem-admm_b200/
+CSRC = os.path.join(_ROOT, "csrc")
+LIB_PATH = os.path.join(_ROOT, "libadmm_b200.so")
+HEADER = os.path.join(os.path.dirname(_ROOT), "include", "admm_b200.h")
+SOURCES = ["api.cu", "projector.cu", "solver_kernels.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+NSCAL = 16
+S_RR0, S_RR1, S_PHP, S_TV, S_GN2, S_IMG, S_MSE = range(7)
+INFO_N, INFO_D, INFO_V, INFO_A, INFO_PART_FLOATS, INFO_FWD_SPAN, INFO_FWD_NREC, INFO_BACK_SPAN, INFO_WS_BYTES = range(9)
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [HEADER]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> libadmm_b200.so (in-tree)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+class State(ctypes.Structure):
+    """struct admm_state (include/admm_b200.h)."""
+    _fields_ = [(k, ctypes.c_void_p) for k in
+                ("x", "r", "p0", "p1", "hp", "rhs0", "tvterm", "atb", "w0", "w1", "rhoD_vec", "rhoD_s", "prec",
+                 "xtrue", "q", "ax", "b", "scal", "part", "counter")] + [
+        ("stride", ctypes.c_longlong), ("rho", ctypes.c_float), ("lam", ctypes.c_float), ("mu", ctypes.c_float),
+        ("q_uniform", ctypes.c_float), ("w_parity", ctypes.c_int), ("fuse_pupdate", ctypes.c_int)]
+
+
+EDGE_FIELDS = ("xi", "xj", "yi", "yj", "z", "ai", "aj", "Wi", "Wj", "qij", "qji")  # struct admm_edge (u64 each)
+PACK_FIELDS = ("x", "y", "out")                                                    # struct admm_pack_item
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _stale():
+        build()
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i, ll, d = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_double
+    L.admm_version.restype = i
+    L.admm_last_error.restype = ctypes.c_char_p
+    L.admm_device_count.restype = i
+    L.admm_launch_count.restype = ll
+    L.admm_plan_create.restype = vp
+    L.admm_plan_create.argtypes = [i, i, d, i, vp, vp, vp, i]
+    L.admm_plan_destroy.argtypes = [vp]
+    L.admm_plan_destroy.restype = None
+    L.admm_plan_info.restype = ll
+    L.admm_plan_info.argtypes = [vp, i]
+    L.admm_forward.argtypes = [vp, vp, ll, i, i, vp, vp]
+    L.admm_adjoint.argtypes = [vp, vp, vp, vp, ll, i, i, vp]
+    L.admm_colnorm2.argtypes = [vp, vp, ll, i, i, vp]
+    L.admm_forward_host.argtypes = [vp, i, vp, vp]
+    L.admm_adjoint_host.argtypes = [vp, i, vp, vp]
+    L.admm_rhs0.argtypes = [vp, ctypes.POINTER(State), vp, vp, vp, vp, i, i, vp]
+    L.admm_x_update.argtypes = [vp, ctypes.POINTER(State), i, i, i, i, vp]
+    L.admm_tv_pass.argtypes = [vp, ctypes.POINTER(State), i, i, i, vp]
+    L.admm_edge_update.argtypes = [vp, ctypes.POINTER(State), vp, i, vp, vp]
+    L.admm_pack.argtypes = [vp, vp, i, vp]
+    L.admm_finalize.argtypes = [vp, ctypes.POINTER(State), vp, vp, vp, vp, i, vp, i, vp, vp]
+    for name in ("admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host", "admm_adjoint_host",
+                 "admm_rhs0", "admm_x_update", "admm_tv_pass", "admm_edge_update", "admm_pack", "admm_finalize"):
+        getattr(L, name).restype = i
+    _lib = L
+    return L
+
+
+EXPORTS = ("admm_version", "admm_last_error", "admm_device_count", "admm_plan_create", "admm_plan_destroy",
+           "admm_plan_info", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host",
+           "admm_adjoint_host", "admm_rhs0", "admm_x_update", "admm_edge_update", "admm_pack", "admm_finalize",
+           "admm_tv_pass", "admm_launch_count")
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib().admm_last_error()
+        raise RuntimeError(f"libadmm_b200 {what} failed ({code}): {msg.decode() if msg else ''}")
+
+
+def require_cuda() -> None:
+    if lib().admm_device_count() < 1:
+        raise RuntimeError("libadmm_b200: no CUDA device visible -- this path is CUDA-only (no CPU fallback)")
+
+
+def launch_count() -> int:
+    return int(lib().admm_launch_count())

@@ -1,0 +1,417 @@
+// api.cu -- extern "C" boundary of libadmm_b200.so (see include/admm_b200.h) and the native host-side
+// drivers that sequence the kernels of one node x-update / one edge sweep.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/admm_b200.h"
+#include "solver_kernels.cuh"
+
+using namespace admm;
+
+static_assert(ADMM_NSCAL == NSCAL, "scalar table width");
+static_assert(sizeof(admm_edge) == sizeof(EdgeDesc), "edge descriptor layout");
+static_assert(sizeof(admm_pack_item) == sizeof(PackDesc), "pack descriptor layout");
+
+namespace admm { long long g_launch_count = 0; }
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(ADMM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+struct admm_plan {
+    int N = 0, D = 0, V = 0, A = 0, device = 0;
+    double det_w = 2.0;
+    std::vector<int> aptr;           // [V+1]
+    std::vector<AngleRec> recs_h;    // [A]
+    AngleRec* d_ang = nullptr;
+    int* d_optr = nullptr;           // [2][V+1]
+    int* d_oidx = nullptr;           // [A]
+    int* d_aptr = nullptr;           // [V+1]
+    int* d_anode = nullptr;          // [A]
+    float* d_recs = nullptr;         // [A][nRec][span]
+    int* d_jstart = nullptr;         // [A][nRec]
+    int nTi = 0, nSeg = 0, span = 0, bspan = 0, max_chunks = 1;
+    long long ws_bytes = 0;
+    // scratch of the host-buffer entry points
+    float* d_himg = nullptr;
+    float* d_hsino = nullptr;
+    int hsino_rows = 0;
+};
+
+extern "C" int admm_version(void) { return 100; }
+extern "C" const char* admm_last_error(void) { return g_err.c_str(); }
+extern "C" long long admm_launch_count(void) { return admm::g_launch_count; }
+extern "C" int admm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static void build_angle_rec(int N, int D, double det_w, float c32, float s32, AngleRec* r) {
+    const double c = (double)c32, s = (double)s32;
+    const double h = 2.0 / N, ds = det_w / D;
+    const bool xdom = std::fabs(c) > std::fabs(s);  // tie -> sin-dominant branch
+    r->ct = c * h / ds;
+    r->st = s * h / ds;
+    const double M = xdom ? r->ct : r->st, m = xdom ? r->st : r->ct;
+    r->inv_major = (float)(1.0 / M);
+    r->slope = (float)(m / M);
+    r->wgt = (float)(h / std::fabs(xdom ? c : s));
+    r->inv_om = (float)(1.0 / std::fabs(M));
+    r->xdom = xdom ? 1 : 0;
+    r->pad = 0;
+}
+
+extern "C" admm_plan* admm_plan_create(int N, int D, double det_w, int V, const int* ang_ptr, const float* cos32,
+                                       const float* sin32, int device) {
+    if (N < 2 || D < 1 || V < 1 || !ang_ptr || !cos32 || !sin32 || det_w <= 0.0) {
+        fail(ADMM_ERR_ARG, "admm_plan_create: bad argument");
+        return nullptr;
+    }
+    if (admm_device_count() <= device) {
+        fail(ADMM_ERR_CUDA, "admm_plan_create: no CUDA device (this library has no CPU fallback)");
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        fail(ADMM_ERR_CUDA, "cudaSetDevice failed");
+        return nullptr;
+    }
+    admm_plan* p = new admm_plan();
+    p->N = N; p->D = D; p->V = V; p->det_w = det_w; p->device = device;
+    p->aptr.assign(ang_ptr, ang_ptr + V + 1);
+    p->A = ang_ptr[V];
+    const int A = p->A;
+    p->recs_h.resize(A > 0 ? A : 1);
+    std::vector<int> optr(2 * (V + 1), 0), oidx(A > 0 ? A : 1, 0), anode(A > 0 ? A : 1, 0);
+    double ext_f = 0.0, ext_b = 0.0;
+    const int Wm = std::min(FW, N), Km = std::min(FSEG, N);
+    for (int a = 0; a < A; ++a) {
+        build_angle_rec(N, D, det_w, cos32[a], sin32[a], &p->recs_h[a]);
+        const AngleRec& r = p->recs_h[a];
+        const double M = std::fabs(r.xdom ? r.ct : r.st), m = std::fabs(r.xdom ? r.st : r.ct);
+        ext_f = std::max(ext_f, (Wm - 1) * M + (Km - 1) * m + 2.0 * M);
+        ext_b = std::max(ext_b, (BTX - 1) * std::fabs(r.ct) + (BTY - 1) * std::fabs(r.st) + 2.0 * std::max(M, 1.0));
+    }
+    p->span = (int)std::ceil(ext_f) + 4;
+    p->bspan = (int)std::ceil(ext_b) + 6;
+    p->nTi = (N + FW - 1) / FW;
+    p->nSeg = (N + FSEG - 1) / FSEG;
+    // orientation lists: [x-dominant angles of node 0..V-1][y-dominant angles of node 0..V-1]
+    int pos = 0;
+    p->max_chunks = 1;
+    for (int o = 0; o < 2; ++o) {
+        for (int v = 0; v < V; ++v) {
+            optr[o * (V + 1) + v] = pos;
+            for (int a = ang_ptr[v]; a < ang_ptr[v + 1]; ++a) {
+                if ((p->recs_h[a].xdom == 1) == (o == 0)) oidx[pos++] = a;
+                anode[a] = v;
+            }
+            const int cnt = pos - optr[o * (V + 1) + v];
+            p->max_chunks = std::max(p->max_chunks, (cnt + FAC - 1) / FAC);
+        }
+        optr[o * (V + 1) + V] = pos;
+    }
+    const size_t nRec = (size_t)p->nTi * p->nSeg;
+    const size_t rec_bytes = (size_t)std::max(A, 1) * nRec * p->span * sizeof(float);
+    const size_t js_bytes = (size_t)std::max(A, 1) * nRec * sizeof(int);
+    bool ok = true;
+    ok &= cudaMalloc(&p->d_ang, sizeof(AngleRec) * std::max(A, 1)) == cudaSuccess;
+    ok &= cudaMalloc(&p->d_optr, sizeof(int) * optr.size()) == cudaSuccess;
+    ok &= cudaMalloc(&p->d_oidx, sizeof(int) * oidx.size()) == cudaSuccess;
+    ok &= cudaMalloc(&p->d_aptr, sizeof(int) * (V + 1)) == cudaSuccess;
+    ok &= cudaMalloc(&p->d_anode, sizeof(int) * anode.size()) == cudaSuccess;
+    ok &= cudaMalloc(&p->d_recs, rec_bytes) == cudaSuccess;
+    ok &= cudaMalloc(&p->d_jstart, js_bytes) == cudaSuccess;
+    if (ok) {
+        ok &= cudaMemcpy(p->d_ang, p->recs_h.data(), sizeof(AngleRec) * std::max(A, 1), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok &= cudaMemcpy(p->d_optr, optr.data(), sizeof(int) * optr.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok &= cudaMemcpy(p->d_oidx, oidx.data(), sizeof(int) * oidx.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok &= cudaMemcpy(p->d_aptr, ang_ptr, sizeof(int) * (V + 1), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok &= cudaMemcpy(p->d_anode, anode.data(), sizeof(int) * anode.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok &= cudaMemset(p->d_jstart, 0, js_bytes) == cudaSuccess;
+        ok &= cudaMemset(p->d_recs, 0, rec_bytes) == cudaSuccess;
+    }
+    if (!ok) {
+        fail(ADMM_ERR_CUDA, std::string("admm_plan_create: ") + cudaGetErrorString(cudaGetLastError()));
+        admm_plan_destroy(p);
+        return nullptr;
+    }
+    p->ws_bytes = (long long)(rec_bytes + js_bytes);
+    return p;
+}
+
+extern "C" void admm_plan_destroy(admm_plan* p) {
+    if (!p) return;
+    cudaFree(p->d_ang); cudaFree(p->d_optr); cudaFree(p->d_oidx); cudaFree(p->d_aptr); cudaFree(p->d_anode);
+    cudaFree(p->d_recs); cudaFree(p->d_jstart); cudaFree(p->d_himg); cudaFree(p->d_hsino);
+    delete p;
+}
+
+extern "C" long long admm_plan_info(const admm_plan* p, int what) {
+    if (!p) return -1;
+    switch (what) {
+        case ADMM_INFO_N: return p->N;
+        case ADMM_INFO_D: return p->D;
+        case ADMM_INFO_V: return p->V;
+        case ADMM_INFO_A: return p->A;
+        case ADMM_INFO_PART_FLOATS: {
+            const long long tiles = (long long)((p->N + 31) / 32) * ((p->N + 31) / 32);
+            return std::max(3 * tiles, 5LL * 4096);
+        }
+        case ADMM_INFO_FWD_SPAN: return p->span;
+        case ADMM_INFO_FWD_NREC: return (long long)p->nTi * p->nSeg;
+        case ADMM_INFO_BACK_SPAN: return p->bspan;
+        case ADMM_INFO_WS_BYTES: return p->ws_bytes;
+    }
+    return -1;
+}
+
+static int check_nodes(const admm_plan* p, int node0, int nodes) {
+    if (!p) return fail(ADMM_ERR_ARG, "null plan");
+    if (node0 < 0 || nodes < 1 || node0 + nodes > p->V) return fail(ADMM_ERR_ARG, "node range outside the plan");
+    return ADMM_OK;
+}
+
+static FwdParams make_fwd(const admm_plan* p, const float* img, long long stride, int node0) {
+    FwdParams P{};
+    P.img = img; P.img_stride = stride; P.ang = p->d_ang; P.optr = p->d_optr; P.oidx = p->d_oidx;
+    P.recs = p->d_recs; P.jstart = p->d_jstart; P.V = p->V; P.node0 = node0; P.N = p->N; P.D = p->D;
+    P.nTi = p->nTi; P.nSeg = p->nSeg; P.span = p->span;
+    P.r = nullptr; P.p_out = nullptr; P.scal = nullptr; P.beta_num = 0; P.beta_den = 0;
+    return P;
+}
+
+static FwdReduceParams make_red(const admm_plan* p, float* sino, int node0, int nodes) {
+    FwdReduceParams R{};
+    R.recs = p->d_recs; R.jstart = p->d_jstart; R.ang = p->d_ang; R.out = sino;
+    R.A0 = p->aptr[node0]; R.A1 = p->aptr[node0 + nodes]; R.D = p->D; R.nRec = p->nTi * p->nSeg; R.span = p->span;
+    return R;
+}
+
+extern "C" int admm_forward(admm_plan* p, const float* d_img, long long stride, int node0, int nodes,
+                            float* d_sino, void* stream) {
+    if (int e = check_nodes(p, node0, nodes)) return e;
+    if (!d_img || !d_sino) return fail(ADMM_ERR_ARG, "admm_forward: null buffer");
+    FwdParams P = make_fwd(p, d_img, stride, node0);
+    CK(launch_forward(P, nodes, p->max_chunks, make_red(p, d_sino, node0, nodes), (cudaStream_t)stream));
+    return ADMM_OK;
+}
+
+static BackParams make_back(const admm_plan* p, const float* q, const float* prec, float* out, long long stride,
+                            int node0) {
+    BackParams B{};
+    B.q = q; B.ang = p->d_ang; B.aptr = p->d_aptr; B.prec = prec; B.out = out; B.stride = stride;
+    B.node0 = node0; B.N = p->N; B.D = p->D; B.bspan = p->bspan;
+    return B;
+}
+
+extern "C" int admm_adjoint(admm_plan* p, const float* d_sino, const float* d_prec, float* d_img, long long stride,
+                            int node0, int nodes, void* stream) {
+    if (int e = check_nodes(p, node0, nodes)) return e;
+    if (!d_img || !d_sino) return fail(ADMM_ERR_ARG, "admm_adjoint: null buffer");
+    CK(launch_back(BACK_PLAIN, make_back(p, d_sino, d_prec, d_img, stride, node0), nodes, (cudaStream_t)stream));
+    return ADMM_OK;
+}
+
+extern "C" int admm_colnorm2(admm_plan* p, float* d_img, long long stride, int node0, int nodes, void* stream) {
+    if (int e = check_nodes(p, node0, nodes)) return e;
+    if (!d_img) return fail(ADMM_ERR_ARG, "admm_colnorm2: null buffer");
+    CK(launch_back(BACK_COLNORM2, make_back(p, nullptr, nullptr, d_img, stride, node0), nodes, (cudaStream_t)stream));
+    return ADMM_OK;
+}
+
+static int host_scratch(admm_plan* p, int rows) {
+    const size_t n = (size_t)p->N * p->N;
+    if (!p->d_himg) CK(cudaMalloc(&p->d_himg, n * sizeof(float)));
+    if (p->hsino_rows < rows) {
+        cudaFree(p->d_hsino);
+        p->d_hsino = nullptr;
+        CK(cudaMalloc(&p->d_hsino, (size_t)rows * p->D * sizeof(float)));
+        p->hsino_rows = rows;
+    }
+    return ADMM_OK;
+}
+
+extern "C" int admm_forward_host(admm_plan* p, int node, const float* h_img, float* h_sino) {
+    if (int e = check_nodes(p, node, 1)) return e;
+    if (!h_img || !h_sino) return fail(ADMM_ERR_ARG, "admm_forward_host: null buffer");
+    CK(cudaSetDevice(p->device));
+    if (int e = host_scratch(p, p->A)) return e;
+    const size_t n = (size_t)p->N * p->N;
+    const int a0 = p->aptr[node], a1 = p->aptr[node + 1];
+    CK(cudaMemcpy(p->d_himg, h_img, n * sizeof(float), cudaMemcpyHostToDevice));
+    // d_hsino is indexed by global angle row like every sinogram array
+    if (int e = admm_forward(p, p->d_himg, (long long)n, node, 1, p->d_hsino, nullptr)) return e;
+    CK(cudaMemcpy(h_sino, p->d_hsino + (size_t)a0 * p->D, (size_t)(a1 - a0) * p->D * sizeof(float), cudaMemcpyDeviceToHost));
+    return ADMM_OK;
+}
+
+extern "C" int admm_adjoint_host(admm_plan* p, int node, const float* h_sino, float* h_img) {
+    if (int e = check_nodes(p, node, 1)) return e;
+    if (!h_img || !h_sino) return fail(ADMM_ERR_ARG, "admm_adjoint_host: null buffer");
+    CK(cudaSetDevice(p->device));
+    if (int e = host_scratch(p, p->A)) return e;
+    const size_t n = (size_t)p->N * p->N;
+    const int a0 = p->aptr[node], a1 = p->aptr[node + 1];
+    CK(cudaMemcpy(p->d_hsino + (size_t)a0 * p->D, h_sino, (size_t)(a1 - a0) * p->D * sizeof(float), cudaMemcpyHostToDevice));
+    if (int e = admm_adjoint(p, p->d_hsino, nullptr, p->d_himg, (long long)n, node, 1, nullptr)) return e;
+    CK(cudaMemcpy(h_img, p->d_himg, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return ADMM_OK;
+}
+
+extern "C" int admm_rhs0(admm_plan* p, const admm_state* s, const int* d_nbr_ptr, const unsigned long long* d_nbr_z,
+                         const unsigned long long* d_nbr_y, const unsigned long long* d_nbr_q, int node0, int nodes,
+                         void* stream) {
+    if (int e = check_nodes(p, node0, nodes)) return e;
+    if (!s || !d_nbr_ptr) return fail(ADMM_ERR_ARG, "admm_rhs0: null argument");
+    RhsParams R{};
+    const long long off = (long long)node0 * s->stride;
+    R.atb = s->atb + off; R.rhs0 = s->rhs0 + off; R.nbr_ptr = d_nbr_ptr; R.nbr_z = d_nbr_z; R.nbr_y = d_nbr_y;
+    R.nbr_q = d_nbr_q; R.stride = s->stride; R.n = (long long)p->N * p->N; R.node0 = node0; R.rho = s->rho;
+    R.q_uniform = s->q_uniform;
+    CK(launch_rhs0(R, nodes, (cudaStream_t)stream));
+    return ADMM_OK;
+}
+
+static TvParams make_tv(const admm_plan* p, const admm_state* s, int node0, bool diag, int parity) {
+    TvParams T{};
+    const long long off = (long long)node0 * s->stride;
+    const float* win = parity ? s->w1 : s->w0;
+    float* wout = parity ? s->w0 : s->w1;
+    T.x = s->x + off; T.w_in = win + 2 * off; T.w_out = wout + 2 * off; T.tvterm = s->tvterm + off;
+    T.r = diag ? s->r + off : nullptr; T.xtrue = s->xtrue; T.stride = s->stride; T.node0 = node0; T.N = p->N;
+    T.lam = s->lam; T.mu = s->mu;
+    T.part = s->part + (long long)node0 * admm_plan_info(p, ADMM_INFO_PART_FLOATS);
+    T.counter = s->counter + node0; T.scal = s->scal;
+    return T;
+}
+
+extern "C" int admm_tv_pass(admm_plan* p, admm_state* s, int node0, int nodes, int with_diag, void* stream) {
+    if (int e = check_nodes(p, node0, nodes)) return e;
+    if (!s) return fail(ADMM_ERR_ARG, "admm_tv_pass: null state");
+    CK(launch_tv(make_tv(p, s, node0, with_diag != 0, s->w_parity), nodes, (cudaStream_t)stream));
+    return ADMM_OK;
+}
+
+extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, int sweeps, int cg_iters,
+                             void* stream) {
+    if (int e = check_nodes(p, node0, nodes)) return e;
+    if (!s || sweeps < 1 || cg_iters < 0) return fail(ADMM_ERR_ARG, "admm_x_update: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)p->N * p->N, off = (long long)node0 * s->stride;
+    const long long part_per = admm_plan_info(p, ADMM_INFO_PART_FLOATS);
+    float* part = s->part + (long long)node0 * part_per;
+    unsigned* counter = s->counter + node0;
+    const int A0 = p->aptr[node0], A1 = p->aptr[node0 + nodes];
+
+    SinoParams SP{};
+    SP.q = s->q; SP.ax = s->ax; SP.b = s->b; SP.anode = p->d_anode; SP.aptr = p->d_aptr; SP.A0 = A0; SP.A1 = A1;
+    SP.D = p->D; SP.node0 = node0; SP.scal = s->scal;
+
+    int parity = s->w_parity;  // the caller flips st->w_parity (sweeps & 1) once every node group is done
+    for (int sw = 0; sw < sweeps; ++sw) {
+        // r = rhs0 + tvterm - H x ; p = r ; rr -> S_RR0 ; ax = A x
+        FwdParams F = make_fwd(p, s->x + off, s->stride, node0);
+        CK(launch_forward(F, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
+        SP.mode = 0;
+        CK(launch_sino_axpy(SP, st));
+        BackParams B = make_back(p, s->q, s->prec, s->r + off, s->stride, node0);
+        B.v = s->x + off; B.rhoD_vec = s->rhoD_vec ? s->rhoD_vec + off : nullptr; B.rhoD_s = s->rhoD_s; B.mu = s->mu;
+        B.rhs0 = s->rhs0 + off; B.tvterm = s->tvterm + off; B.p_out = s->p0 + off;
+        B.part = part; B.counter = counter; B.scal = s->scal; B.dot_slot = S_RR0;
+        CK(launch_back(BACK_RESID0, B, nodes, st));
+        int cur = 0;
+        for (int it = 0; it < cg_iters; ++it) {
+            const int rr_in = (it & 1) ? S_RR1 : S_RR0, rr_out = (it & 1) ? S_RR0 : S_RR1;
+            float* pcur = (cur ? s->p1 : s->p0) + off;
+            float* poth = (cur ? s->p0 : s->p1) + off;
+            if (it > 0) {
+                if (s->fuse_pupdate) {
+                    FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
+                    Fp.r = s->r + off; Fp.p_out = poth; Fp.scal = s->scal; Fp.beta_num = rr_in; Fp.beta_den = rr_out;
+                    CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
+                    cur ^= 1;
+                    pcur = poth;
+                } else {
+                    CgParams U{};
+                    U.r = s->r + off; U.p = pcur; U.p_out = poth; U.stride = s->stride; U.n = n; U.node0 = node0;
+                    U.rr_in = rr_out; U.rr_out = rr_in;  // beta = scal[rr_in(it)] / scal[rr_out(it)] = new / old
+                    U.scal = s->scal;
+                    CK(launch_p_update(U, nodes, st));
+                    cur ^= 1;
+                    pcur = poth;
+                    FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
+                    CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
+                }
+            } else {
+                FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
+                CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
+            }
+            BackParams H = make_back(p, s->q, s->prec, s->hp + off, s->stride, node0);
+            H.v = pcur; H.rhoD_vec = B.rhoD_vec; H.rhoD_s = s->rhoD_s; H.mu = s->mu;
+            H.part = part; H.counter = counter; H.scal = s->scal; H.dot_slot = S_PHP;
+            CK(launch_back(BACK_HP, H, nodes, st));
+            SP.mode = 1; SP.rr_in = rr_in;
+            CK(launch_sino_axpy(SP, st));
+            CgParams U{};
+            U.x = s->x + off; U.r = s->r + off; U.p = pcur; U.hp = s->hp + off; U.stride = s->stride; U.n = n;
+            U.node0 = node0; U.rr_in = rr_in; U.rr_out = rr_out; U.part = part; U.counter = counter; U.scal = s->scal;
+            long long nb = (n / 4 + 256 * 4 - 1) / (256 * 4);
+            nb = std::max(1LL, std::min(nb, 4096LL));
+            CK(launch_cg_update(U, nodes, (int)nb, st));
+        }
+        CK(launch_tv(make_tv(p, s, node0, true, parity), nodes, st));
+        parity ^= 1;
+    }
+    CK(launch_sino_resid(SP, nodes, st));
+    return ADMM_OK;
+}
+
+extern "C" int admm_edge_update(admm_plan* p, const admm_state* s, const admm_edge* d_edges, int nedges,
+                                double* d_sums, void* stream) {
+    if (!p || !s) return fail(ADMM_ERR_ARG, "admm_edge_update: null argument");
+    if (nedges <= 0) return ADMM_OK;
+    EdgeParams E{};
+    E.edges = reinterpret_cast<const EdgeDesc*>(d_edges); E.n = (long long)p->N * p->N; E.q_uniform = s->q_uniform;
+    E.part = s->part; E.counter = s->counter; E.sums = d_sums;
+    long long nb = (E.n + 256 * 4 - 1) / (256 * 4);
+    nb = std::max(1LL, std::min(nb, 1024LL));
+    // part: 5 floats per block per edge must fit the per-unit budget
+    if (nb * 5 > admm_plan_info(p, ADMM_INFO_PART_FLOATS)) nb = admm_plan_info(p, ADMM_INFO_PART_FLOATS) / 5;
+    // per-edge workspace stride is nb*5 floats (<= PART_FLOATS)
+    CK(launch_edges(E, nedges, (int)nb, (cudaStream_t)stream));
+    return ADMM_OK;
+}
+
+extern "C" int admm_pack(admm_plan* p, const admm_pack_item* d_items, int nitems, void* stream) {
+    if (!p) return fail(ADMM_ERR_ARG, "admm_pack: null plan");
+    PackParams K{};
+    K.items = reinterpret_cast<const PackDesc*>(d_items); K.n = (long long)p->N * p->N;
+    CK(launch_pack(K, nitems, (cudaStream_t)stream));
+    return ADMM_OK;
+}
+
+extern "C" int admm_finalize(admm_plan* p, const admm_state* s, const double* d_sums, const int* d_edge_gi,
+                             const int* d_edge_gj, const int* d_edge_flags, int nedges, const int* d_node_gid, int Vg,
+                             double* d_row, void* stream) {
+    if (!p || !s || !d_row || !d_node_gid) return fail(ADMM_ERR_ARG, "admm_finalize: null argument");
+    FinalizeParams F{};
+    F.sums = d_sums; F.edge_gi = d_edge_gi; F.edge_gj = d_edge_gj; F.edge_flags = d_edge_flags; F.scal = s->scal;
+    F.node_gid = d_node_gid; F.row = d_row; F.E = nedges; F.V = p->V; F.Vg = Vg; F.rho = s->rho;
+    CK(launch_finalize(F, (cudaStream_t)stream));
+    return ADMM_OK;
+}

@@ -1,0 +1,106 @@
+// common.cuh -- shared device helpers for the sm_100a TV-ADMM tomography kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace admm {
+
+extern long long g_launch_count;  // kernels launched by this library (bench evidence)
+
+// Per-angle geometry record (built on the host in fp64 from the fp32-rounded (cos, sin) table so the CUDA
+// kernels and the fp64 oracle take bit-identical dominant-axis decisions).
+// Pixel (ix, iy) projects to fractional detector bin
+//     tau = cj + (ix - cx) * ct + (iy - cx) * st,   cx = (N-1)/2, cj = (D-1)/2,
+// with ct = cos * h/ds, st = sin * h/ds (h = 2/N pixel size, ds = det_w/D bin size).
+struct AngleRec {
+    double ct, st;
+    float inv_major;  // 1 / major,  major = xdom ? ct : st
+    float slope;      // minor / major
+    float wgt;        // h / |a|, a = xdom ? cos : sin   (Joseph step length)
+    float inv_om;     // 1 / |major| = 1 / omega  (hat half-width in bins is omega)
+    int xdom;         // 1: |cos| > |sin| -> step along iy, interpolate along ix
+    int pad;
+};
+static_assert(sizeof(AngleRec) == 40, "AngleRec layout is part of the C ABI");
+
+constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23 : (v + kMagic) - kMagic == rint(v) for |v| < 2^22
+constexpr int kMagicBits = 0x4B400000;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum of K floats per thread; result valid in thread 0.  red must hold K * 32 floats.
+template <int K>
+__device__ __forceinline__ void block_sum(float (&v)[K], float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) red[k * 32 + wid] = v[k];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float t = (lane < nw) ? red[k * 32 + lane] : 0.f;
+            v[k] = warp_sum(t);
+        }
+    }
+}
+
+// Deterministic grid reduction ("last block done"): every block stores K partials, the last block to
+// arrive sums all partials of its group in a fixed order in fp64 and writes out[0..K).  The counter is
+// reset by the last block so the workspace is reusable by the next launch on the same stream.
+//   part:    [nblk][K] floats for this group;  counter: one unsigned for this group.
+// Must be called by all threads of the block; v[] valid in thread 0 (output of block_sum).
+template <int K>
+__device__ __forceinline__ void grid_reduce_store(const float (&v)[K], float* part, unsigned* counter,
+                                                  int blk, int nblk, double* out, float* red) {
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) part[(size_t)blk * K + k] = v[k];
+        __threadfence();
+        const unsigned t = atomicAdd(counter, 1u);
+        s_last = (t == (unsigned)nblk - 1u);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        // fixed-order fp64 accumulation: thread t sums partials t, t+T, ... then a fixed tree
+        double acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.0;
+        for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] += (double)__ldcg(&part[(size_t)b * K + k]);
+        }
+        double* dred = reinterpret_cast<double*>(red);  // red holds >= 32*K floats -> reuse per k
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double a = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            __syncthreads();
+            if (lane == 0) dred[wid] = a;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double s = 0.0;
+                for (int w = 0; w < nw; ++w) s += dred[w];
+                out[k] = s;
+            }
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+}  // namespace admm

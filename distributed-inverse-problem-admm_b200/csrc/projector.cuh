@@ -1,0 +1,93 @@
+// projector.cuh -- launch parameter blocks of the Joseph projector kernels (K1, K2, K2b).
+#pragma once
+#include "common.cuh"
+
+namespace admm {
+
+// ---- K1 forward: strip/segment decomposition ----------------------------------------------------
+constexpr int FW = 120;       // interpolation-axis extent of a strip (pixels)
+constexpr int FL = 32;        // steps per staged slab
+constexpr int FSEG = 256;     // steps per block segment (8 slabs)
+constexpr int FTPA = 128;     // threads per angle slot (bins handled per round)
+constexpr int FAC = 16;       // angles per block chunk
+constexpr int FTHREADS = 256; // 2 angle slots
+constexpr int FPITCH = FW + 3;  // smem row pitch (odd): [-1 halo][0..FW)[2 zero columns]
+
+struct FwdParams {
+    const float* img;        // [nodes][N*N] images to project (p or x)
+    long long img_stride;    // floats between node images
+    const AngleRec* ang;     // [A] angle records of this rank (sinogram row order)
+    const int* optr;         // [2][V+1] ranges into oidx per orientation (0: xdom, 1: ydom)
+    const int* oidx;         // angle row ids grouped by (orientation, node)
+    float* recs;             // [A][nRec][span] partial line integrals
+    int* jstart;             // [A][nRec] first bin of each record
+    int V;                   // nodes in optr tables
+    int node0;               // first node of this launch
+    int N, D;
+    int nTi, nSeg, span;
+    // optional fused CG direction update p_new = r + beta * p_old (img = p_old)
+    const float* r;          // [nodes][N*N] or nullptr
+    float* p_out;            // [nodes][N*N]
+    const double* scal;      // [V][NSCAL] node scalars
+    int beta_num, beta_den;  // scalar slots: beta = scal[beta_num] / scal[beta_den]
+};
+
+struct FwdReduceParams {
+    const float* recs;
+    const int* jstart;
+    const AngleRec* ang;
+    float* out;              // [A][D] sinogram rows
+    int A0, A1;              // angle row range
+    int D, nRec, span;
+    // optional fused axpy: acc_out[a][j] (+)= coef(node) * out  (Ax recurrence), node_of_angle lookup
+};
+
+// ---- K2 back-projection (gather) with fused epilogues ---------------------------------------------
+constexpr int BTX = 32;        // tile rows (ix)
+constexpr int BTY = 32;        // tile cols (iy)
+constexpr int BTHREADS = 256;  // 4 pixels (along iy) per thread
+constexpr int BAC = 16;        // angles staged per chunk
+
+enum BackMode : int {
+    BACK_PLAIN = 0,    // out = A^T (prec * q)
+    BACK_HP = 1,       // out = A^T(prec q) + rhoD*v + mu*K^T K v ; scal[dot_slot] = <v, out>
+    BACK_RESID0 = 2,   // r = rhs0 + tvterm - H v ; p = r ; scal[dot_slot] = <r, r>
+    BACK_COLNORM2 = 3  // out = sum_rays A[r,p]^2  (q unused)
+};
+
+struct BackParams {
+    const float* q;          // [A][D] sinogram rows (angle-major)
+    const AngleRec* ang;
+    const int* aptr;         // [V+1] angle row ranges per node
+    const float* prec;       // [V] per-node measurement precision P_i (nullptr = 1)
+    float* out;              // [nodes][N*N]  (Hp / r / plain)
+    long long stride;        // floats between node images (all image arrays share it)
+    int node0, N, D, bspan;
+    // epilogue inputs
+    const float* v;          // p (BACK_HP) or x (BACK_RESID0)
+    const float* rhoD_vec;   // [nodes][N*N] or nullptr
+    const float* rhoD_s;     // [V] scalar rho*D_i (used when rhoD_vec == nullptr)
+    float mu;
+    const float* rhs0;       // BACK_RESID0
+    const float* tvterm;     // BACK_RESID0
+    float* p_out;            // BACK_RESID0: p = r
+    // reduction workspace
+    float* part;             // [V][nblk] partials
+    unsigned* counter;       // [V]
+    double* scal;            // [V][NSCAL]
+    int dot_slot;
+};
+
+constexpr int NSCAL = 16;  // doubles per node in the scalar table
+// scalar slots
+enum ScalSlot : int {
+    S_RR0 = 0, S_RR1 = 1,   // <r,r> ping-pong by CG iteration parity
+    S_PHP = 2,              // <p, Hp>
+    S_TV = 3,               // canonical TV(x)
+    S_GN2 = 4,              // |g|^2 stationarity
+    S_IMG = 5,              // |x - x_true|^2
+    S_MSE = 6,              // |Ax - b|^2
+    S_ALPHA = 7             // last alpha (diagnostic)
+};
+
+}  // namespace admm

@@ -1,0 +1,89 @@
+// solver_kernels.cuh -- parameter blocks of K3-K6 and the bookkeeping kernels.
+#pragma once
+#include "projector.cuh"
+
+namespace admm {
+
+struct TvParams {
+    const float* x;        // [nodes][n]
+    const float* w_in;     // [nodes][2][n] split-Bregman multiplier (old)
+    float* w_out;          // [nodes][2][n] (new; must not alias w_in)
+    float* tvterm;         // [nodes][n] in: mu K^T(d-w) used by the last solve; out: the new one
+    const float* r;        // [nodes][n] final CG residual (nullptr: skip the stationarity diagnostic)
+    const float* xtrue;    // [n] or nullptr
+    long long stride;
+    int node0, N;
+    float lam, mu;
+    float* part; unsigned* counter; double* scal;
+};
+
+struct CgParams {
+    float* x; float* r; const float* p; const float* hp; float* p_out;
+    long long stride, n;
+    int node0, rr_in, rr_out;
+    float* part; unsigned* counter; double* scal;
+};
+
+struct SinoParams {
+    const float* q; float* ax; const float* b;
+    const int* anode;      // [A] node of each angle row
+    const int* aptr;       // [V+1]
+    int A0, A1, D, node0, mode, rr_in;   // mode 0: ax = q ; 1: ax += alpha q
+    double* scal;
+};
+
+struct RhsParams {
+    const float* atb; float* rhs0;
+    const int* nbr_ptr;                 // [V+1] CSR over G.neighbors(i) order
+    const unsigned long long* nbr_z;    // [nnz] device address of z_ij
+    const unsigned long long* nbr_y;    // [nnz] device address of y_ij,i
+    const unsigned long long* nbr_q;    // [nnz] device address of Q_ij or 0 (uniform)
+    long long stride, n;
+    int node0;
+    float rho, q_uniform;
+};
+
+struct EdgeDesc {
+    unsigned long long xi, xj;   // x of each end (0: remote end)
+    unsigned long long yi, yj;   // scaled duals of the local ends
+    unsigned long long z;        // consensus variable (replicated on both owners of a cut edge)
+    unsigned long long ai, aj;   // received a = x + y of a remote end
+    unsigned long long Wi, Wj;   // per-pixel precisions for the W-weighted fusion (0: midpoint)
+    unsigned long long qij, qji; // Q vectors for the penalty value (0: uniform)
+};
+
+struct EdgeParams {
+    const EdgeDesc* edges;
+    long long n;
+    float q_uniform;
+    float* part; unsigned* counter; double* sums;   // sums: [E][5]
+};
+
+struct PackDesc { unsigned long long x, y, out; };
+struct PackParams { const PackDesc* items; long long n; };
+
+struct FinalizeParams {
+    const double* sums;       // [E][5]
+    const int* edge_gi;       // [E] global node ids
+    const int* edge_gj;
+    const int* edge_flags;    // bit0: i local, bit1: j local, bit2: owns the dual residual
+    const double* scal;       // [V][NSCAL]
+    const int* node_gid;      // [V]
+    double* row;              // [2 + 7*Vg]
+    int E, V, Vg;
+    float rho;
+};
+
+cudaError_t launch_forward(const FwdParams& P, int nodes, int max_chunks, const FwdReduceParams& R, cudaStream_t st);
+cudaError_t launch_back(int mode, const BackParams& P, int nodes, cudaStream_t st);
+cudaError_t launch_tv(const TvParams& P, int nodes, cudaStream_t st);
+cudaError_t launch_cg_update(const CgParams& P, int nodes, int nblk, cudaStream_t st);
+cudaError_t launch_p_update(const CgParams& P, int nodes, cudaStream_t st);
+cudaError_t launch_sino_axpy(const SinoParams& P, cudaStream_t st);
+cudaError_t launch_sino_resid(const SinoParams& P, int nodes, cudaStream_t st);
+cudaError_t launch_rhs0(const RhsParams& P, int nodes, cudaStream_t st);
+cudaError_t launch_edges(const EdgeParams& P, int nedges, int nblk, cudaStream_t st);
+cudaError_t launch_pack(const PackParams& P, int nitems, cudaStream_t st);
+cudaError_t launch_finalize(const FinalizeParams& P, cudaStream_t st);
+
+}  // namespace admm

@@ -1,0 +1,149 @@
+/*
+ * admm_b200.h -- C ABI of libadmm_b200.so: the B200-native (sm_100a) hot path of the decentralized
+ * TV-ADMM tomography solve of prsinha1/Distributed-Inverse-Problem-Admm.
+ *
+ * The reference has no FFI: its boundary is Python module + function signatures.
+ * These entry points are what a ctypes binding inside the reference's block_2/3/5/6 modules binds (see
+ * INTEGRATION.md); each cites the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void*; all `d_` pointers are
+ *     device pointers owned by the caller (PyTorch in the shipped host code); the library allocates only
+ *     inside admm_plan_create (geometry tables + projector workspace) and frees in admm_plan_destroy;
+ *   - every function returns 0 on success, a negative code otherwise; admm_last_error() gives the text;
+ *   - images are float32 [node][ix*N + iy] (axis 0 = x), sinograms float32 [angle row][D] angle-major,
+ *     exactly the layouts of `A_dense_list[i] @ x` / `sinograms[i].reshape(-1)`
+ *     (block_6_admm_loop_ver2.py:46,145,193);
+ *   - no CPU fallback exists: without a CUDA device every compute entry point fails with ADMM_ERR_CUDA.
+ */
+#ifndef ADMM_B200_H
+#define ADMM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADMM_OK 0
+#define ADMM_ERR_ARG (-1)
+#define ADMM_ERR_CUDA (-2)
+
+#define ADMM_NSCAL 16 /* doubles per node in the scalar table */
+/* scalar-table slots (per node) */
+#define ADMM_S_RR0 0
+#define ADMM_S_RR1 1
+#define ADMM_S_PHP 2
+#define ADMM_S_TV 3
+#define ADMM_S_GN2 4
+#define ADMM_S_IMG 5
+#define ADMM_S_MSE 6
+
+typedef struct admm_plan admm_plan; /* opaque: geometry of the nodes resident on one GPU */
+
+/* Device-resident state of the nodes / edges owned by one rank.  Arrays are [V][...] over the plan's
+ * local nodes with `stride` floats between node images. */
+typedef struct admm_state {
+    float* x;                 /* [V][n]  iterates x_i                      (block_6_ver2:36)            */
+    float* r;                 /* [V][n]  CG residual                                                    */
+    float* p0;                /* [V][n]  CG direction (ping)                                            */
+    float* p1;                /* [V][n]  CG direction (pong)                                            */
+    float* hp;                /* [V][n]  H p                                                            */
+    float* rhs0;              /* [V][n]  A^T P b + rho sum_j Q_ij (z_ij - y_ij,i)                       */
+    float* tvterm;            /* [V][n]  mu K^T (d - w)                                                 */
+    const float* atb;         /* [V][n]  A^T P b                                                        */
+    float* w0;                /* [V][2][n] TV multiplier (ping)                                         */
+    float* w1;                /* [V][2][n] TV multiplier (pong)                                         */
+    const float* rhoD_vec;    /* [V][n] rho * sum_j Q_ij, or NULL when Q is uniform                     */
+    const float* rhoD_s;      /* [V] rho * deg_i * q (uniform Q)                                        */
+    const float* prec;        /* [V] node measurement precisions P_i, or NULL (= 1)                     */
+    const float* xtrue;       /* [n] ground truth for img_mse (block_6_ver2:199-206), or NULL           */
+    float* q;                 /* [A][D] scratch sinogram A p                                            */
+    float* ax;                /* [A][D] A x (kept current by recurrence)                                */
+    const float* b;           /* [A][D] measured sinograms b_i (block_6_ver2:46)                        */
+    double* scal;             /* [V][ADMM_NSCAL] node scalars                                           */
+    float* part;              /* reduction workspace, admm_plan_info(plan, ADMM_INFO_PART_FLOATS) floats*/
+    unsigned* counter;        /* reduction workspace, max(V, E) zero-initialised counters               */
+    long long stride;         /* floats between node images (>= n)                                      */
+    float rho, lam, mu, q_uniform;
+    int w_parity;             /* 0: w0 current, 1: w1 current (caller flips it by sweeps&1 after x-updates) */
+    int fuse_pupdate;         /* 1: fuse p = r + beta p into the forward projector                      */
+} admm_state;
+
+/* One undirected edge (i<j) as seen by this rank; addresses are device pointers as integers. */
+typedef struct admm_edge {
+    unsigned long long xi, xj, yi, yj, z, ai, aj, Wi, Wj, qij, qji;
+} admm_edge;
+
+typedef struct admm_pack_item { unsigned long long x, y, out; } admm_pack_item;
+
+int admm_version(void);
+const char* admm_last_error(void);
+int admm_device_count(void); /* 0 when no CUDA device is visible (never throws) */
+
+/* ---- geometry ---------------------------------------------------------------------------------------
+ * Replaces odl.uniform_discr / uniform_partition / Parallel2dGeometry / RayTransform construction in
+ * _build_parallel_beam_operators (block_2_load_odl_data.py:16-65) and generate_sinogram
+ * (Gen_Sino_Partitioned.py:124-134).  `ang_ptr[V+1]` gives each node's angle-row range, `cos32/sin32`
+ * are the fp32-rounded trig values of every angle row (computed in fp64 on the host). */
+admm_plan* admm_plan_create(int N, int D, double det_w, int V, const int* ang_ptr, const float* cos32,
+                            const float* sin32, int device);
+void admm_plan_destroy(admm_plan* plan);
+#define ADMM_INFO_N 0
+#define ADMM_INFO_D 1
+#define ADMM_INFO_V 2
+#define ADMM_INFO_A 3
+#define ADMM_INFO_PART_FLOATS 4   /* floats of `part` needed per unit (node or edge) */
+#define ADMM_INFO_FWD_SPAN 5
+#define ADMM_INFO_FWD_NREC 6
+#define ADMM_INFO_BACK_SPAN 7
+#define ADMM_INFO_WS_BYTES 8
+long long admm_plan_info(const admm_plan* plan, int what);
+
+/* ---- K1 / K2 / K2b: the operator  (device pointers) ---------------------------------------------------
+ * admm_forward  : `Ai @ x` / op(x)            block_6_admm_loop_ver2.py:145,193; block_2_load_odl_data.py:149
+ * admm_adjoint  : `Ai.T @ r`                  block_6_admm_loop_ver2.py:145   (plain transpose; prec may be NULL)
+ * admm_colnorm2 : np.sum(A_i*A_i, axis=0)     block_3_graph_and_precisions.py:22 */
+int admm_forward(admm_plan* plan, const float* d_img, long long stride, int node0, int nodes,
+                 float* d_sino, void* stream);
+int admm_adjoint(admm_plan* plan, const float* d_sino, const float* d_prec, float* d_img, long long stride,
+                 int node0, int nodes, void* stream);
+int admm_colnorm2(admm_plan* plan, float* d_img, long long stride, int node0, int nodes, void* stream);
+
+/* same, HOST buffers (copies inside; one node) -- what `op(x).asarray()` costs a NumPy caller */
+int admm_forward_host(admm_plan* plan, int node, const float* h_img, float* h_sino);
+int admm_adjoint_host(admm_plan* plan, int node, const float* h_sino, float* h_img);
+
+/* ---- K6: rhs0_i = A^T P b_i + rho sum_j Q_ij (z_ij - y_ij,i)   block_6_admm_loop_ver2.py:87-95 ----------
+ * nbr_* are device arrays over the CSR neighbour lists (G.neighbors(i) order): addresses of z_ij, of
+ * y_ij,i and of Q_ij (0 = uniform). */
+int admm_rhs0(admm_plan* plan, const admm_state* st, const int* d_nbr_ptr, const unsigned long long* d_nbr_z,
+              const unsigned long long* d_nbr_y, const unsigned long long* d_nbr_q, int node0, int nodes,
+              void* stream);
+
+/* ---- K1+K2+K3+K4: node x-update  (replaces build_node_problem + prob.solve, block_5_node_problem.py:6-32,
+ * block_6_admm_loop_ver2.py:97-176): `sweeps` x [ `cg_iters` CG iterations on
+ * (A^T P A + rho D + mu K^T K) x = rhs0 + mu K^T(d - w) ; d = shrink2(Kx + w, lam/mu) ; w += Kx - d ].
+ * Leaves per-node TV(x), |g|^2, |x-x_true|^2, |Ax-b|^2 in the scalar table. */
+int admm_x_update(admm_plan* plan, admm_state* st, int node0, int nodes, int sweeps, int cg_iters,
+                  void* stream);
+
+/* ---- K5: edges   block_6_admm_loop_ver2.py:210-264 -------------------------------------------------------
+ * d_sums[E][5] = |x_i-z'|^2, |x_j-z'|^2, |z'-z|^2, pen_i, pen_j per edge. */
+int admm_edge_update(admm_plan* plan, const admm_state* st, const admm_edge* d_edges, int nedges,
+                     double* d_sums, void* stream);
+int admm_pack(admm_plan* plan, const admm_pack_item* d_items, int nitems, void* stream);
+/* history row [r2, s2, pri_node[Vg], dual_node[Vg], pen[Vg], mse[Vg], tv[Vg], gn2[Vg], img[Vg]] (doubles) */
+int admm_finalize(admm_plan* plan, const admm_state* st, const double* d_sums, const int* d_edge_gi,
+                  const int* d_edge_gj, const int* d_edge_flags, int nedges, const int* d_node_gid, int Vg,
+                  double* d_row, void* stream);
+
+/* ---- block_4 helpers on device (block_4_tv_helpers.py:17-46): one TV pass without a CG solve ------------
+ * used by the drop-in block_4 module; outputs w', tvterm' and TV(x) like the fused K3. */
+int admm_tv_pass(admm_plan* plan, admm_state* st, int node0, int nodes, int with_diag, void* stream);
+
+/* launches issued by this library since load (the bench's gpu_launches evidence) */
+long long admm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADMM_B200_H */
