@@ -1,0 +1,343 @@
+"""Device-resident decentralized TV-ADMM engine (block_6_admm_loop_ver2.py:15-326 on the GPU).
+
+All state (x_i, z_ij, y_ij,*, CG vectors, TV multipliers, sinograms) lives in HBM for the whole solve; Python only
+sequences C-ABI calls into libadmm_b200.so and, when the graph is sharded, the NCCL send/recv of cut-edge iterates
+and the one all-reduce of the residual row.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+from . import _native as nat
+from .operators import Plan
+from .sharding import ShardPlan, build_shard_plan, exchange
+
+
+def _torch():
+    import torch
+    return torch
+
+
+HIST_KEYS = ("primal", "dual", "pri_per_node", "dual_per_node", "obj_per_node", "obj_total", "mse_sino_per_node",
+             "mse_sino_total", "img_mse_per_node", "img_mse_total", "g_norm_history", "eps_used_history",
+             "eps_target_history")
+
+
+class ADMMEngine:
+    """One rank's share of the solve.
+
+    thetas      per global node angle arrays (radians)
+    sinograms   per global node (M_i, D) arrays (only the local ones are uploaded)
+    G           networkx graph on 0..V-1
+    Q           None / float -> uniform Q_ij = q (D_i = deg_i q);  callable (i, j) -> n-vector otherwise
+    Wi_list     per-pixel precisions W_i, used only when weighted_z (PDF eq. (2))
+    """
+
+    def __init__(self, thetas, sinograms, G, N, D=None, det_w=2.0, lam_tv=0.01, rho=1.0, Q=None, Wi_list=None,
+                 node_prec=None, tv_mu=None, tv_sweeps=1, cg_iters=8, phantom_true=None, weighted_z=False,
+                 device=0, dist=None, rank=0, world=1, group=None, node_group=None, fuse_pupdate=True,
+                 max_iters=200):
+        torch = _torch()
+        nat.require_cuda()
+        self.torch = torch
+        self.dev = torch.device(f"cuda:{device}")
+        torch.cuda.set_device(self.dev)
+        self.N, self.n = int(N), int(N) * int(N)
+        self.D = int(D if D is not None else N)
+        self.rho, self.lam = float(rho), float(lam_tv)
+        self.mu = float(tv_mu if tv_mu is not None else rho)
+        self.S, self.C = int(tv_sweeps), int(cg_iters)
+        self.dist, self.rank, self.world, self.group = dist, int(rank), int(world), group
+        self.sp: ShardPlan = build_shard_plan(G, self.world, self.rank)
+        sp = self.sp
+        self.Vg = sp.V
+        self.loc = sp.local_nodes
+        V = self.V = len(self.loc)
+        if V == 0:
+            raise ValueError("rank owns no node (more ranks than nodes)")
+        n = self.n
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.plan = Plan(N, [thetas[g] for g in self.loc], self.D, det_w, device)
+        A = self.A = self.plan.A
+        self.node_group = int(node_group) if node_group else V
+
+        # ---- data ------------------------------------------------------------------------------------
+        b = np.concatenate([np.asarray(sinograms[g], dtype=np.float32).reshape(-1, self.D) for g in self.loc], axis=0)
+        if b.shape != (A, self.D):
+            raise ValueError(f"sinograms of the local nodes have shape {b.shape}, expected {(A, self.D)}")
+        self.b = torch.from_numpy(np.ascontiguousarray(b)).to(self.dev)
+        self.h2d_bytes = b.nbytes
+        self.prec = None
+        if node_prec is not None:
+            self.prec = torch.tensor([float(node_prec[g]) for g in self.loc], **f32)
+        self.atb = torch.empty(V, n, **f32)
+        self.plan.adjoint(self.b, self.atb, prec=self.prec)
+        self.xtrue = None
+        if phantom_true is not None:
+            self.xtrue = torch.from_numpy(np.ascontiguousarray(np.asarray(phantom_true, dtype=np.float32).reshape(-1))).to(self.dev)
+            self.h2d_bytes += self.xtrue.numel() * 4
+
+        # ---- Q: uniform scalar or per directed edge vectors -----------------------------------------------
+        deg = [int(sp.nbr_ptr[g + 1] - sp.nbr_ptr[g]) for g in self.loc]
+        self.q_uniform = 1.0
+        self.Qdir = None
+        nnz_loc = sum(deg)
+        if Q is None or np.isscalar(Q):
+            self.q_uniform = 1.0 if Q is None else float(Q)
+        else:
+            qv = []
+            for g in self.loc:
+                for k in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1]):
+                    qv.append(np.asarray(Q(g, int(sp.nbr_idx[k])), dtype=np.float32).reshape(-1))
+            first = qv[0][0] if qv else 1.0
+            if all(np.all(q == first) for q in qv):
+                self.q_uniform = float(first)
+            else:
+                self.Qdir = torch.from_numpy(np.stack(qv)).to(self.dev)
+                self.h2d_bytes += self.Qdir.numel() * 4
+        self.rhoD_s = torch.tensor([self.rho * d * self.q_uniform for d in deg], **f32)
+        self.rhoD_vec = None
+        if self.Qdir is not None:
+            self.rhoD_vec = torch.zeros(V, n, **f32)
+            k = 0
+            for li, d in enumerate(deg):
+                for _ in range(d):
+                    self.rhoD_vec[li] += self.Qdir[k]
+                    k += 1
+            self.rhoD_vec *= self.rho
+
+        # ---- state ---------------------------------------------------------------------------------------
+        z = lambda *s: torch.zeros(*s, **f32)  # noqa: E731
+        self.x, self.r, self.p0, self.p1, self.hp = z(V, n), z(V, n), z(V, n), z(V, n), z(V, n)
+        self.rhs0, self.tvterm = z(V, n), z(V, n)
+        self.w0, self.w1 = z(V, 2, n), z(V, 2, n)
+        self.q, self.ax = z(A, self.D), z(A, self.D)
+        self.scal = torch.zeros(V, nat.NSCAL, dtype=torch.float64, device=self.dev)
+        E = self.E = len(sp.local_edges)
+        units = max(V, E, 1)
+        self.part = z(units * self.plan.part_floats)
+        self.counter = torch.zeros(units, dtype=torch.int32, device=self.dev)
+        self.z = z(max(E, 1), n)
+        self.y = z(max(E, 1), 2, n)
+        self.sums = torch.zeros(max(E, 1), 5, dtype=torch.float64, device=self.dev)
+        self.row = torch.zeros(2 + 7 * self.Vg, dtype=torch.float64, device=self.dev)
+        self.max_iters = int(max_iters)
+        self.hist = torch.zeros(self.max_iters, 2 + 7 * self.Vg, dtype=torch.float64, device=self.dev)
+        self.W = None
+        if weighted_z:
+            if Wi_list is None:
+                raise ValueError("weighted_z needs Wi_list")
+            need = sorted({g for le in sp.local_edges for g in (le.gi, le.gj)})
+            self.Wmap = {g: k for k, g in enumerate(need)}
+            self.W = torch.from_numpy(np.stack([np.asarray(Wi_list[g], dtype=np.float32).reshape(-1) for g in need])).to(self.dev)
+
+        # exchange buffers (cut edges), one contiguous block per peer
+        self.send = {p: z(len(sp.exch[p]), n) for p in sp.peers}
+        self.recv = {p: z(len(sp.exch[p]), n) for p in sp.peers}
+
+        self._build_tables()
+        self.st = nat.State()
+        self._fill_state(fuse_pupdate)
+        self.k = 0
+        torch.cuda.synchronize(self.dev)
+
+    # ----------------------------------------------------------------------------------------------------
+    def _addr(self, t, *idx):
+        off = 0
+        for i, s in zip(idx, t.stride()):
+            off += i * s
+        return t.data_ptr() + off * t.element_size()
+
+    def _build_tables(self):
+        torch, sp = self.torch, self.sp
+        # K6 neighbour tables (G.neighbors(i) order of every local node)
+        ptr, za, ya, qa = [0], [], [], []
+        k = 0
+        for g in self.loc:
+            for kk in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1]):
+                slot = sp.eslot[int(sp.nbr_edge[kk])]
+                za.append(self._addr(self.z, slot))
+                ya.append(self._addr(self.y, slot, int(sp.nbr_end[kk])))
+                qa.append(self._addr(self.Qdir, k) if self.Qdir is not None else 0)
+                k += 1
+            ptr.append(len(za))
+        self.dirslot = {}
+        k = 0
+        for g in self.loc:
+            for kk in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1]):
+                self.dirslot[(g, int(sp.nbr_idx[kk]))] = k
+                k += 1
+        i64 = lambda a: torch.tensor(a if len(a) else [0], dtype=torch.int64, device=self.dev)  # noqa: E731
+        self.nbr_ptr = torch.tensor(ptr, dtype=torch.int32, device=self.dev)
+        self.nbr_z, self.nbr_y, self.nbr_q = i64(za), i64(ya), i64(qa)
+        # K5 edge descriptors, pack items, finalize tables
+        ed, gi, gj, fl, packs = [], [], [], [], []
+        for le in sp.local_edges:
+            s = le.slot
+            xi = self._addr(self.x, sp.g2l[le.gi]) if le.i_local else 0
+            xj = self._addr(self.x, sp.g2l[le.gj]) if le.j_local else 0
+            yi = self._addr(self.y, s, 0) if le.i_local else 0
+            yj = self._addr(self.y, s, 1) if le.j_local else 0
+            ai = self._addr(self.recv[le.peer], le.xslot) if not le.i_local else 0
+            aj = self._addr(self.recv[le.peer], le.xslot) if not le.j_local else 0
+            Wi = self._addr(self.W, self.Wmap[le.gi]) if self.W is not None else 0
+            Wj = self._addr(self.W, self.Wmap[le.gj]) if self.W is not None else 0
+            qij = self._addr(self.Qdir, self.dirslot[(le.gi, le.gj)]) if (self.Qdir is not None and le.i_local) else 0
+            qji = self._addr(self.Qdir, self.dirslot[(le.gj, le.gi)]) if (self.Qdir is not None and le.j_local) else 0
+            ed.append([xi, xj, yi, yj, self._addr(self.z, s), ai, aj, Wi, Wj, qij, qji])
+            gi.append(le.gi)
+            gj.append(le.gj)
+            fl.append((1 if le.i_local else 0) | (2 if le.j_local else 0) | (4 if le.owns_dual else 0))
+            if le.peer >= 0:
+                if le.i_local:
+                    packs.append([xi, yi, self._addr(self.send[le.peer], le.xslot)])
+                else:
+                    packs.append([xj, yj, self._addr(self.send[le.peer], le.xslot)])
+        self.edge_desc = torch.tensor(ed if ed else [[0] * 11], dtype=torch.int64, device=self.dev)
+        i32 = lambda a: torch.tensor(a if len(a) else [0], dtype=torch.int32, device=self.dev)  # noqa: E731
+        self.edge_gi, self.edge_gj, self.edge_fl = i32(gi), i32(gj), i32(fl)
+        self.node_gid = i32(self.loc)
+        self.pack_desc = torch.tensor(packs if packs else [[0, 0, 0]], dtype=torch.int64, device=self.dev)
+        self.n_pack = len(packs)
+
+    def _fill_state(self, fuse):
+        st = self.st
+        for name in ("x", "r", "p0", "p1", "hp", "rhs0", "tvterm", "atb", "w0", "w1", "q", "ax", "b", "scal", "part",
+                     "counter", "rhoD_s"):
+            setattr(st, name, getattr(self, name).data_ptr())
+        st.rhoD_vec = self.rhoD_vec.data_ptr() if self.rhoD_vec is not None else None
+        st.prec = self.prec.data_ptr() if self.prec is not None else None
+        st.xtrue = self.xtrue.data_ptr() if self.xtrue is not None else None
+        st.stride = self.n
+        st.rho, st.lam, st.mu, st.q_uniform = self.rho, self.lam, self.mu, self.q_uniform
+        st.w_parity = 0
+        st.fuse_pupdate = 1 if fuse else 0
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    # ---- one outer iteration ------------------------------------------------------------------------------
+    def nodes_phase(self):
+        """rhs0 assembly (K6) + x-updates (K1-K4) of every local node, node group by node group."""
+        L, h, st = nat.lib(), self.plan.handle, self.st
+        sref = ctypes.byref(st)
+        nat.check(L.admm_rhs0(h, sref, self.nbr_ptr.data_ptr(), self.nbr_z.data_ptr(), self.nbr_y.data_ptr(),
+                              self.nbr_q.data_ptr(), 0, self.V, self._stream()), "admm_rhs0")
+        for n0 in range(0, self.V, self.node_group):
+            nn = min(self.node_group, self.V - n0)
+            nat.check(L.admm_x_update(h, sref, n0, nn, self.S, self.C, self._stream()), "admm_x_update")
+        st.w_parity ^= (self.S & 1)
+
+    def exchange_phase(self):
+        if self.n_pack:
+            nat.check(nat.lib().admm_pack(self.plan.handle, self.pack_desc.data_ptr(), self.n_pack, self._stream()),
+                      "admm_pack")
+            exchange(self.dist, self.sp, self.send, self.recv, self.group)
+
+    def edges_phase(self):
+        L, h = nat.lib(), self.plan.handle
+        sref = ctypes.byref(self.st)
+        nat.check(L.admm_edge_update(h, sref, self.edge_desc.data_ptr(), self.E, self.sums.data_ptr(), self._stream()),
+                  "admm_edge_update")
+        nat.check(L.admm_finalize(h, sref, self.sums.data_ptr(), self.edge_gi.data_ptr(), self.edge_gj.data_ptr(),
+                                  self.edge_fl.data_ptr(), self.E, self.node_gid.data_ptr(), self.Vg,
+                                  self.row.data_ptr(), self._stream()), "admm_finalize")
+        if self.world > 1:
+            self.dist.all_reduce(self.row, group=self.group)  # the only collective
+        if self.k < self.max_iters:
+            self.hist[self.k].copy_(self.row)
+
+    def step(self):
+        self.nodes_phase()
+        self.exchange_phase()
+        self.edges_phase()
+        self.k += 1
+
+    # ---- results --------------------------------------------------------------------------------------------
+    def residuals(self):
+        """(primal, dual) norms of the last completed iteration -- forces a device sync."""
+        r = self.row[:2].cpu().numpy()
+        return math.sqrt(r[0]), math.sqrt(r[1])
+
+    def history(self, iters=None):
+        """History dict with the keys of block_6_admm_loop_ver2.py:310-326 (one entry per iteration)."""
+        iters = self.k if iters is None else iters
+        H = self.hist[:iters].cpu().numpy()
+        Vg = self.Vg
+        sl = lambda k: H[:, 2 + k * Vg: 2 + (k + 1) * Vg]  # noqa: E731
+        pri, dual, pen, mse, tv, gn2, img = (sl(k) for k in range(7))
+        prec = np.ones(Vg)
+        out = {k: [] for k in HIST_KEYS}
+        obj = 0.5 * self._prec_global()[None, :] * mse + self.lam * tv + 0.5 * self.rho * pen
+        for k in range(iters):
+            eps_target = 2.0 / ((k + 1) ** 1.005)  # block_6_admm_loop_ver2.py:101-103
+            out["primal"].append(math.sqrt(H[k, 0]))
+            out["dual"].append(math.sqrt(H[k, 1]))
+            out["pri_per_node"].append(np.sqrt(pri[k]))
+            out["dual_per_node"].append(np.sqrt(dual[k]))
+            out["obj_per_node"].append(obj[k].copy())
+            out["obj_total"].append(float(np.sum(obj[k])))
+            out["mse_sino_per_node"].append(mse[k].copy())
+            out["mse_sino_total"].append(float(np.sum(mse[k])))
+            out["img_mse_per_node"].append(img[k].copy())
+            out["img_mse_total"].append(float(np.sum(img[k])))
+            out["g_norm_history"].append(np.sqrt(gn2[k]))
+            out["eps_used_history"].append(np.full(Vg, min(1e-2, eps_target)))
+            out["eps_target_history"].append(np.full(Vg, eps_target))
+        del prec
+        return out
+
+    def _prec_global(self):
+        p = np.ones(self.Vg)
+        if getattr(self, "_node_prec_all", None) is not None:
+            p = np.asarray(self._node_prec_all, dtype=np.float64)
+        return p
+
+    def x_local(self):
+        return self.x.cpu().numpy()
+
+    def x_all(self):
+        """x of every node on every rank (list of V arrays of length n, float64 like the reference's)."""
+        xl = self.x
+        if self.world == 1:
+            arr = xl.cpu().numpy()
+            return [arr[i].astype(np.float64) for i in range(self.V)]
+        torch = self.torch
+        counts = [sum(1 for r in self.sp.node_rank if r == k) for k in range(self.world)]
+        mx = max(counts)
+        pad = torch.zeros(mx, self.n, dtype=torch.float32, device=self.dev)
+        pad[: self.V] = xl
+        bufs = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(bufs, pad, group=self.group)
+        out = []
+        for k in range(self.world):
+            a = bufs[k][: counts[k]].cpu().numpy()
+            out.extend(a[i].astype(np.float64) for i in range(counts[k]))
+        return out
+
+    def close(self):
+        self.plan.close()
+
+
+def solve(engine: ADMMEngine, max_iters, eps_pri, eps_dual, verbose=False, stop=True, check_every=1,
+          snapshot=None):
+    """Run the outer loop with the reference's stop test (block_6_admm_loop_ver2.py:286-289)."""
+    done = 0
+    for k in range(max_iters):
+        engine.step()
+        done = k + 1
+        need = (stop and ((k + 1) % check_every == 0)) or (verbose and k % 10 == 0)
+        if need:
+            pri, dual = engine.residuals()
+            if verbose and k % 10 == 0:
+                print(f"iter {k}, primal {pri:.3e}, dual {dual:.3e}")
+            if stop and pri < eps_pri and dual < eps_dual:
+                if verbose:
+                    print(f"stopped at iter {k}, primal {pri:.3e}, dual {dual:.3e}")
+                break
+        if snapshot is not None:
+            snapshot(k, engine)
+    return done

@@ -1,0 +1,125 @@
+"""Drop-in for the reference's block_6_admm_loop_ver2.py (the live ADMM loop, :15-326) and, through
+block_6_admm_loop.py, for the skeleton's extended signature (block_6_admm_loop.py:72-84).
+
+Same call, same return `(x_list, history)`, same history keys (:310-326); the body runs on the GPU:
+node x-updates are TV-split + CG solves of eq. (1) (block_5_node_problem.py:21-29) in hand-written sm_100a
+kernels instead of CVXPY->SCS on a dense matrix, the z / y / residual loop (:210-264) is one fused edge kernel.
+CUDA-only: without a device the call raises (no CPU fallback).
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+
+from admm_b200.solver import ADMMEngine, solve
+
+# SCS-era kwargs of the skeleton (block_6_admm_loop.py:72-84) and of test_final_integration.py:31 that have no
+# meaning for the CUDA solver: accepted and ignored so existing drivers run unchanged.
+_IGNORED = ("scs_total_iters", "scs_chunk_iters", "scs_snapshot_dir", "scs_use_indirect", "scs_alpha",
+            "scs_acceleration", "scs_lookback", "scs_scale", "scs_save_every_chunks", "edge_mask_provider")
+
+
+def _node_geometry(A_list):
+    """Per-node angle arrays and the common (N, D, det_w) from operator-shaped `A_dense_list` entries."""
+    thetas = []
+    geo = None
+    for A in A_list:
+        if not hasattr(A, "angles"):
+            raise TypeError(
+                "A_dense_list entries must be matrix-free RayTransformCUDA operators (block_2_load_odl_data."
+                "load_odl_data builds them); dense matrices carry no geometry and there is no CPU/dense path")
+        g = (A.N, A.D, A.det_w)
+        if geo is None:
+            geo = g
+        elif g != geo:
+            raise ValueError("all node operators must share N, D and the detector width")
+        thetas.append(np.asarray(A.angles, dtype=np.float64))
+    return thetas, geo
+
+
+def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
+                       N, lam_tv=0.01, rho=1.0,
+                       max_iters=10, max_inner_iters=100,
+                       eps_pri=1e-1, eps_dual=1e-1,
+                       verbose=True, snapshot_dir=None,
+                       snapshot_every=None, snapshot_div=10, phantom_true=None,
+                       # --- B200 solver controls (not in the reference) ---
+                       cg_iters=8, tv_sweeps=1, tv_mu=None, node_prec=None, weighted_z=False, scs_eps=None,
+                       check_every=1, node_group=None, fuse_pupdate=True, device=None, return_engine=False,
+                       **kwargs):
+    """Returns x_per_node as list of reconstructions, each length n, and the history of residual norms
+    (block_6_admm_loop_ver2.py:21-24).
+
+    `max_inner_iters` caps the CG iterations per TV sweep (it is unused in the reference, :17); `cg_iters`,
+    `tv_sweeps`, `tv_mu` select the inner work, which is fixed per outer iteration (no host round trips).
+    `Qij_diag_fn` may be a callable (i, j) -> n-vector (block_3 provider), a scalar, or None (uniform 1).
+    Under torch.distributed (NCCL) the nodes are sharded over the ranks; every rank returns the full result.
+    """
+    for k in list(kwargs):
+        if k in _IGNORED:
+            kwargs.pop(k)
+    if kwargs:
+        raise TypeError(f"decentralized_admm() got unexpected keyword arguments {sorted(kwargs)}")
+    if G is None:
+        raise ValueError("G is None: build_pixel_connected_Q_provider returns a graph only with plot_union=True "
+                         "in the reference (SURVEY App. B-8); this build always returns one")
+    num_nodes = len(A_dense_list)
+    thetas, (Ng, D, det_w) = _node_geometry(A_dense_list)
+    if Ng != N:
+        raise ValueError(f"N={N} does not match the operators' image size {Ng}")
+    n = N * N
+    if A_dense_list[0].shape[1] != n:
+        raise ValueError("operator domain size mismatch")
+
+    if snapshot_dir is not None:
+        os.makedirs(snapshot_dir, exist_ok=True)
+    if snapshot_every is None:
+        snapshot_every = max(1, max_iters // snapshot_div)  # :31-32
+
+    import torch
+    import torch.distributed as dist
+    world, rank, group = 1, 0, None
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        world, rank = dist.get_world_size(), dist.get_rank()
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else torch.cuda.current_device()
+
+    eng = ADMMEngine(thetas, sinograms, G, N, D=D, det_w=det_w, lam_tv=lam_tv, rho=rho, Q=Qij_diag_fn,
+                     Wi_list=Wi_list, node_prec=node_prec, tv_mu=tv_mu, tv_sweeps=tv_sweeps,
+                     cg_iters=min(int(cg_iters), int(max_inner_iters)), phantom_true=phantom_true,
+                     weighted_z=weighted_z, device=device, dist=dist if world > 1 else None, rank=rank, world=world,
+                     group=group, node_group=node_group, fuse_pupdate=fuse_pupdate, max_iters=max_iters)
+    eng._node_prec_all = node_prec
+
+    print(f"Max ADMM Iteration in Block-6 B4 Loop = {max_iters}") if verbose else None
+
+    def snapshot(k, e):  # :269-281 (npy only; PNGs need matplotlib, which the hot path does not import)
+        if snapshot_dir is not None and ((k + 1) % snapshot_every == 0) and rank == 0:
+            for i, xi in enumerate(e.x_all()):
+                np.save(os.path.join(snapshot_dir, f"iter_{k+1:04d}_node_{i}.npy"), xi.reshape(N, N))
+
+    t0 = time.perf_counter()
+    iters = solve(eng, max_iters, eps_pri, eps_dual, verbose=verbose, stop=True, check_every=check_every,
+                  snapshot=snapshot if snapshot_dir is not None else None)
+    x = eng.x_all()
+    history = eng.history(iters)
+    history["primal_res"], history["dual_res"], history["obj"] = history["primal"], history["dual"], history["obj_total"]
+    history["wall_time_s"] = time.perf_counter() - t0
+    history["inner"] = {"cg_iters": eng.C, "tv_sweeps": eng.S, "tv_mu": eng.mu}
+
+    try:  # :293-306
+        log_dir = snapshot_dir if snapshot_dir is not None else None
+        if log_dir is not None and rank == 0:
+            with open(os.path.join(log_dir, "admm_internal_params.txt"), "w") as f:
+                f.write("===== ADMM Internal Parameters =====\n")
+                f.write(f"rho = {rho}\nlambda_tv = {lam_tv}\nNumber of nodes = {num_nodes}\n")
+                f.write(f"cg_iters = {eng.C}\ntv_sweeps = {eng.S}\ntv_mu = {eng.mu}\n")
+    except Exception as e:  # pragma: no cover
+        print(f"[WARN] Could not save internal params: {e}")
+
+    if return_engine:
+        return x, history, eng
+    eng.close()
+    return x, history

@@ -1,0 +1,93 @@
+"""GPU parity of the full decentralized TV-ADMM loop against the fp64 oracle (same phantom, angles, graph, rho,
+lambda, inner iteration counts), through the drop-in block_6 boundary."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TRACE_TOL = 1e-3   # north_star: per-iteration primal/dual residual traces within 1e-3 relative
+RECON_TOL = 1e-3   # final reconstruction within 1e-3 relative L2
+PSNR_TOL = 0.05    # dB
+
+
+def _problem(N, M, V, partition="contiguous", sigma=0.005, hetero=False):
+    from admm_b200 import RayTransformCUDA, node_angles
+    from oracle import oracle as O
+    thetas = node_angles(M, V, partition)
+    img = O.shepp_logan(N)
+    ops_o = [O.JosephOperator(N, t) for t in thetas]
+    sinos = []
+    for i, op in enumerate(ops_o):
+        s_i = sigma * (2.0 ** ((i % 4) - 1)) if hetero else sigma
+        e = np.random.default_rng(1234 + i).standard_normal(op.shape[0])
+        sinos.append((op.forward(img) + s_i * e).reshape(op.nang, op.D).astype(np.float32))
+    ops_g = [RayTransformCUDA(N, t) for t in thetas]
+    return thetas, img, ops_o, ops_g, sinos
+
+
+def _compare(hg, ho, xg, xo, img, N, iters):
+    assert len(hg["primal"]) == len(ho["primal"]) == iters
+    pg, po = np.array(hg["primal"]), np.array(ho["primal"])
+    dg, do = np.array(hg["dual"]), np.array(ho["dual"])
+    assert np.max(np.abs(pg - po) / po) < TRACE_TOL
+    assert np.max(np.abs(dg - do) / do) < TRACE_TOL
+    for key in ("pri_per_node", "dual_per_node", "mse_sino_per_node", "obj_per_node", "img_mse_per_node"):
+        a, b = np.array(hg[key]), np.array(ho[key])
+        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-12)) < 2e-3, key
+    a, b = np.array(hg["g_norm_history"]), np.array(ho["g_norm_history"])
+    assert np.max(np.abs(a - b) / np.maximum(b, 1e-9)) < 1e-2
+    from oracle import oracle as O
+    for i in range(len(xo)):
+        assert np.linalg.norm(xg[i] - xo[i]) / np.linalg.norm(xo[i]) < RECON_TOL
+        assert abs(O.psnr(xg[i].reshape(N, N), img) - O.psnr(xo[i].reshape(N, N), img)) < PSNR_TOL
+
+
+def test_ring_uniform_q_200_iterations():
+    """BASELINE cfg-1 shape (ring of 4, uniform Q, lam 0.02, rho 2) at N=64, 200 outer iterations."""
+    from block_6_admm_loop_ver2 import decentralized_admm
+    from oracle import oracle as O
+    N, M, V, iters = 64, 180, 4, 200
+    thetas, img, ops_o, ops_g, sinos = _problem(N, M, V)
+    G = O.make_graph("ring", V)
+    kw = dict(lam_tv=0.02, rho=2.0, max_iters=iters, eps_pri=0.0, eps_dual=0.0, phantom_true=img)
+    xo, ho = O.decentralized_admm(ops_o, sinos, G, None, None, N, uniform_q=1.0, tv_sweeps=1, cg_iters=8, **kw)
+    xg, hg = decentralized_admm(ops_g, sinos, G, None, None, N, verbose=False, cg_iters=8, tv_sweeps=1, **kw)
+    _compare(hg, ho, xg, xo, img, N, iters)
+    assert np.stack(xg).shape == (V, N * N)
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+def test_regular_graph_w_precisions_weighted(fuse):
+    """block_3 arithmetic-mean Q from column norms, heterogeneous node precisions, W-weighted z (PDF eq. 2),
+    reference_literal angle sets (both projector orientations in every node), 2 TV sweeps."""
+    from block_6_admm_loop_ver2 import decentralized_admm
+    from oracle import oracle as O
+    N, M, V, iters = 48, 96, 6, 40
+    thetas, img, ops_o, ops_g, sinos = _problem(N, M, V, "reference_literal", hetero=True)
+    G = O.make_graph("regular", V, seed=0, degree=3)
+    Wi, Q = O.make_precisions([op.colnorm2() for op in ops_o], "arithmetic")
+    sig = np.array([0.005 * 2.0 ** ((i % 4) - 1) for i in range(V)])
+    prec = (sig ** -2) / np.max(sig ** -2)
+    kw = dict(lam_tv=0.002, rho=2.0, max_iters=iters, eps_pri=0.0, eps_dual=0.0, phantom_true=img,
+              node_prec=prec, weighted_z=True, tv_sweeps=2, cg_iters=6, tv_mu=0.05)
+    xo, ho = O.decentralized_admm(ops_o, sinos, G, Wi, Q, N, **kw)
+    xg, hg = decentralized_admm(ops_g, sinos, G, Wi, Q, N, verbose=False, fuse_pupdate=fuse, **kw)
+    _compare(hg, ho, xg, xo, img, N, iters)
+
+
+def test_stop_test_and_node_groups():
+    """Stop test (block_6_admm_loop_ver2.py:286-289) fires at the same iteration as the oracle; node-group
+    scheduling (L2 blocking) does not change the numbers."""
+    from block_6_admm_loop_ver2 import decentralized_admm
+    from oracle import oracle as O
+    N, M, V = 32, 60, 5
+    thetas, img, ops_o, ops_g, sinos = _problem(N, M, V)
+    G = O.make_graph("path", V)
+    kw = dict(lam_tv=0.02, rho=2.0, max_iters=60, eps_pri=0.3, eps_dual=0.3, phantom_true=img)
+    xo, ho = O.decentralized_admm(ops_o, sinos, G, None, None, N, uniform_q=1.0, **kw)
+    xg, hg = decentralized_admm(ops_g, sinos, G, None, None, N, verbose=False, **kw)
+    assert 1 < len(ho["primal"]) < 60
+    assert len(hg["primal"]) == len(ho["primal"])
+    xg2, hg2 = decentralized_admm(ops_g, sinos, G, None, None, N, verbose=False, node_group=2, **kw)
+    assert hg2["primal"] == hg["primal"] and hg2["dual"] == hg["dual"]
+    assert all(np.array_equal(a, b) for a, b in zip(xg, xg2))
