@@ -89,7 +89,9 @@ def lib():
     L.admm_edge_update.argtypes = [vp, ctypes.POINTER(State), vp, i, vp, vp]
     L.admm_pack.argtypes = [vp, vp, i, vp]
     L.admm_finalize.argtypes = [vp, ctypes.POINTER(State), vp, vp, vp, vp, i, vp, i, vp, vp]
-    for name in ("admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host", "admm_adjoint_host",
+    L.admm_profile_enable.argtypes = [i]
+    L.admm_profile_read.argtypes = [vp, vp]
+    for name in ("admm_profile_enable", "admm_profile_read", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host", "admm_adjoint_host",
                  "admm_rhs0", "admm_x_update", "admm_tv_pass", "admm_edge_update", "admm_pack", "admm_finalize"):
         getattr(L, name).restype = i
     _lib = L
@@ -99,7 +101,23 @@ def lib():
 EXPORTS = ("admm_version", "admm_last_error", "admm_device_count", "admm_plan_create", "admm_plan_destroy",
            "admm_plan_info", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host",
            "admm_adjoint_host", "admm_rhs0", "admm_x_update", "admm_edge_update", "admm_pack", "admm_finalize",
-           "admm_tv_pass", "admm_launch_count")
+           "admm_tv_pass", "admm_launch_count", "admm_profile_enable", "admm_profile_read")
+
+KC_NAMES = ("fwd", "fwd_reduce", "back_plain", "back_hp", "back_resid0", "colnorm2", "tv", "cg_update", "p_update",
+            "sino_axpy", "sino_resid", "rhs0", "edge", "pack", "finalize", "fwd_fused")
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().admm_profile_enable(1 if on else 0), "admm_profile_enable")
+
+
+def profile_read() -> dict:
+    """{kernel class: (launches, total ms)} since the last read (synchronises the device)."""
+    n = len(KC_NAMES)
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_longlong * n)()
+    check(lib().admm_profile_read(ms, cnt), "admm_profile_read")
+    return {KC_NAMES[k]: (int(cnt[k]), float(ms[k])) for k in range(n) if cnt[k]}
 
 
 def check(code: int, what: str = "") -> None:

@@ -300,12 +300,16 @@ class ADMMEngine:
         return self.x.cpu().numpy()
 
     def x_all(self):
-        """x of every node on every rank (list of V arrays of length n, float64 like the reference's)."""
+        """x of every node on every rank: list of V float32 arrays of length n (views of one pinned host buffer;
+        the reference's are float64 -- `np.stack`, `.reshape(N, N)` and arithmetic behave the same)."""
         xl = self.x
-        if self.world == 1:
-            arr = xl.cpu().numpy()
-            return [arr[i].astype(np.float64) for i in range(self.V)]
         torch = self.torch
+        if self.world == 1:
+            host = torch.empty(xl.shape, dtype=torch.float32, pin_memory=True)
+            host.copy_(xl, non_blocking=True)
+            torch.cuda.synchronize(self.dev)
+            arr = host.numpy()
+            return [arr[i] for i in range(self.V)]
         counts = [sum(1 for r in self.sp.node_rank if r == k) for k in range(self.world)]
         mx = max(counts)
         pad = torch.zeros(mx, self.n, dtype=torch.float32, device=self.dev)
@@ -315,7 +319,7 @@ class ADMMEngine:
         out = []
         for k in range(self.world):
             a = bufs[k][: counts[k]].cpu().numpy()
-            out.extend(a[i].astype(np.float64) for i in range(counts[k]))
+            out.extend(a[i] for i in range(counts[k]))
         return out
 
     def close(self):

@@ -12,10 +12,49 @@
 using namespace admm;
 
 static_assert(ADMM_NSCAL == NSCAL, "scalar table width");
+static_assert(ADMM_KC_COUNT == admm::KC_COUNT, "kernel class count");
 static_assert(sizeof(admm_edge) == sizeof(EdgeDesc), "edge descriptor layout");
 static_assert(sizeof(admm_pack_item) == sizeof(PackDesc), "pack descriptor layout");
 
-namespace admm { long long g_launch_count = 0; }
+namespace admm {
+long long g_launch_count = 0;
+bool g_prof_on = false;
+struct ProfRec { int kc; cudaEvent_t e0, e1; };
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_pool;
+static cudaEvent_t prof_event() {
+    if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_mark(int kc, cudaStream_t st, bool begin) {
+    if (begin) {
+        ProfRec r{kc, prof_event(), prof_event()};
+        cudaEventRecord(r.e0, st);
+        g_prof.push_back(r);
+    } else if (!g_prof.empty()) {
+        cudaEventRecord(g_prof.back().e1, st);
+    }
+}
+}  // namespace admm
+
+extern "C" int admm_profile_enable(int on) {
+    admm::g_prof_on = (on != 0);
+    return ADMM_OK;
+}
+// Synchronises the device, adds the elapsed ms and launch counts of every recorded launch to ms[kc] / cnt[kc]
+// (arrays of ADMM_KC_COUNT) and clears the record list.
+extern "C" int admm_profile_read(double* ms, long long* cnt) {
+    if (!ms || !cnt) return ADMM_ERR_ARG;
+    if (cudaDeviceSynchronize() != cudaSuccess) return ADMM_ERR_CUDA;
+    for (auto& r : admm::g_prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms[r.kc] += t; cnt[r.kc] += 1; }
+        admm::g_pool.push_back(r.e0);
+        admm::g_pool.push_back(r.e1);
+    }
+    admm::g_prof.clear();
+    return ADMM_OK;
+}
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {

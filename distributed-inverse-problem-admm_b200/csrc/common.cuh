@@ -7,6 +7,19 @@ namespace admm {
 
 extern long long g_launch_count;  // kernels launched by this library (bench evidence)
 
+// kernel classes for the optional CUDA-event profiler (admm_profile_* in the C ABI)
+enum KClass : int {
+    KC_FWD = 0, KC_FWD_REDUCE, KC_BACK_PLAIN, KC_BACK_HP, KC_BACK_RESID0, KC_COLNORM, KC_TV, KC_CG_UPDATE,
+    KC_P_UPDATE, KC_SINO_AXPY, KC_SINO_RESID, KC_RHS0, KC_EDGE, KC_PACK, KC_FINALIZE, KC_FWD_FUSED, KC_COUNT
+};
+void prof_mark(int kc, cudaStream_t st, bool begin);
+extern bool g_prof_on;
+struct ProfScope {  // records a CUDA event pair around one launch on its own stream when profiling is on
+    int kc; cudaStream_t st;
+    ProfScope(int k, cudaStream_t s) : kc(k), st(s) { ++g_launch_count; if (g_prof_on) prof_mark(kc, st, true); }
+    ~ProfScope() { if (g_prof_on) prof_mark(kc, st, false); }
+};
+
 // Per-angle geometry record (built on the host in fp64 from the fp32-rounded (cos, sin) table so the CUDA
 // kernels and the fp64 oracle take bit-identical dominant-axis decisions).
 // Pixel (ix, iy) projects to fractional detector bin

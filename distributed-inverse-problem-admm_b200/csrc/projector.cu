@@ -372,9 +372,9 @@ cudaError_t launch_forward(const FwdParams& P, int nodes, int max_chunks, const 
         configured_span = P.span;
     }
     dim3 grid(P.nTi * P.nSeg * max_chunks, nodes, 2);
-    ++g_launch_count; fwd_strip_kernel<<<grid, FTHREADS, smem, st>>>(P);
+    { ProfScope ps(P.r ? KC_FWD_FUSED : KC_FWD, st); fwd_strip_kernel<<<grid, FTHREADS, smem, st>>>(P); }
     dim3 rgrid((R.D + 255) / 256, R.A1 - R.A0);
-    if (rgrid.y > 0) { ++g_launch_count; fwd_reduce_kernel<<<rgrid, 256, 0, st>>>(R); }
+    if (rgrid.y > 0) { ProfScope ps(KC_FWD_REDUCE, st); fwd_reduce_kernel<<<rgrid, 256, 0, st>>>(R); }
     return cudaGetLastError();
 }
 
@@ -384,10 +384,10 @@ cudaError_t launch_back(int mode, const BackParams& P, int nodes, cudaStream_t s
     const size_t smem = f * sizeof(float) + BAC * sizeof(float4);
     dim3 grid((P.N + BTY - 1) / BTY, (P.N + BTX - 1) / BTX, nodes);
     switch (mode) {
-        case BACK_PLAIN: ++g_launch_count; back_tile_kernel<BACK_PLAIN><<<grid, BTHREADS, smem, st>>>(P); break;
-        case BACK_HP: ++g_launch_count; back_tile_kernel<BACK_HP><<<grid, BTHREADS, smem, st>>>(P); break;
-        case BACK_RESID0: ++g_launch_count; back_tile_kernel<BACK_RESID0><<<grid, BTHREADS, smem, st>>>(P); break;
-        case BACK_COLNORM2: ++g_launch_count; back_tile_kernel<BACK_COLNORM2><<<grid, BTHREADS, smem, st>>>(P); break;
+        case BACK_PLAIN: { ProfScope ps(KC_BACK_PLAIN, st); back_tile_kernel<BACK_PLAIN><<<grid, BTHREADS, smem, st>>>(P); } break;
+        case BACK_HP: { ProfScope ps(KC_BACK_HP, st); back_tile_kernel<BACK_HP><<<grid, BTHREADS, smem, st>>>(P); } break;
+        case BACK_RESID0: { ProfScope ps(KC_BACK_RESID0, st); back_tile_kernel<BACK_RESID0><<<grid, BTHREADS, smem, st>>>(P); } break;
+        case BACK_COLNORM2: { ProfScope ps(KC_COLNORM, st); back_tile_kernel<BACK_COLNORM2><<<grid, BTHREADS, smem, st>>>(P); } break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

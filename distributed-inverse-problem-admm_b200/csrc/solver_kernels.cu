@@ -334,42 +334,42 @@ static inline int stream_blocks(long long n, int per_thread) {
 
 cudaError_t launch_tv(const TvParams& P, int nodes, cudaStream_t st) {
     dim3 grid((P.N + TT - 1) / TT, (P.N + TT - 1) / TT, nodes);
-    ++g_launch_count; tv_fused_kernel<<<grid, 256, 0, st>>>(P);
+    { ProfScope ps(KC_TV, st); tv_fused_kernel<<<grid, 256, 0, st>>>(P); }
     return cudaGetLastError();
 }
 cudaError_t launch_cg_update(const CgParams& P, int nodes, int nblk, cudaStream_t st) {
-    ++g_launch_count; cg_update_kernel<<<dim3(nblk, nodes), 256, 0, st>>>(P);
+    { ProfScope ps(KC_CG_UPDATE, st); cg_update_kernel<<<dim3(nblk, nodes), 256, 0, st>>>(P); }
     return cudaGetLastError();
 }
 cudaError_t launch_p_update(const CgParams& P, int nodes, cudaStream_t st) {
-    ++g_launch_count; p_update_kernel<<<dim3(stream_blocks(P.n, 8), nodes), 256, 0, st>>>(P);
+    { ProfScope ps(KC_P_UPDATE, st); p_update_kernel<<<dim3(stream_blocks(P.n, 8), nodes), 256, 0, st>>>(P); }
     return cudaGetLastError();
 }
 cudaError_t launch_sino_axpy(const SinoParams& P, cudaStream_t st) {
     if (P.A1 <= P.A0) return cudaSuccess;
-    ++g_launch_count; sino_axpy_kernel<<<dim3((P.D + 255) / 256, P.A1 - P.A0), 256, 0, st>>>(P);
+    { ProfScope ps(KC_SINO_AXPY, st); sino_axpy_kernel<<<dim3((P.D + 255) / 256, P.A1 - P.A0), 256, 0, st>>>(P); }
     return cudaGetLastError();
 }
 cudaError_t launch_sino_resid(const SinoParams& P, int nodes, cudaStream_t st) {
-    ++g_launch_count; sino_resid_kernel<<<nodes, 256, 0, st>>>(P);
+    { ProfScope ps(KC_SINO_RESID, st); sino_resid_kernel<<<nodes, 256, 0, st>>>(P); }
     return cudaGetLastError();
 }
 cudaError_t launch_rhs0(const RhsParams& P, int nodes, cudaStream_t st) {
-    ++g_launch_count; rhs0_kernel<<<dim3(stream_blocks(P.n, 4), nodes), 256, 0, st>>>(P);
+    { ProfScope ps(KC_RHS0, st); rhs0_kernel<<<dim3(stream_blocks(P.n, 4), nodes), 256, 0, st>>>(P); }
     return cudaGetLastError();
 }
 cudaError_t launch_edges(const EdgeParams& P, int nedges, int nblk, cudaStream_t st) {
     if (nedges <= 0) return cudaSuccess;
-    ++g_launch_count; edge_kernel<<<dim3(nblk, nedges), 256, 0, st>>>(P);
+    { ProfScope ps(KC_EDGE, st); edge_kernel<<<dim3(nblk, nedges), 256, 0, st>>>(P); }
     return cudaGetLastError();
 }
 cudaError_t launch_pack(const PackParams& P, int nitems, cudaStream_t st) {
     if (nitems <= 0) return cudaSuccess;
-    ++g_launch_count; pack_kernel<<<dim3(stream_blocks(P.n, 4), nitems), 256, 0, st>>>(P);
+    { ProfScope ps(KC_PACK, st); pack_kernel<<<dim3(stream_blocks(P.n, 4), nitems), 256, 0, st>>>(P); }
     return cudaGetLastError();
 }
 cudaError_t launch_finalize(const FinalizeParams& P, cudaStream_t st) {
-    ++g_launch_count; finalize_kernel<<<1, 32, 0, st>>>(P);
+    { ProfScope ps(KC_FINALIZE, st); finalize_kernel<<<1, 32, 0, st>>>(P); }
     return cudaGetLastError();
 }
 

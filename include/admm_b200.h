@@ -143,6 +143,13 @@ int admm_tv_pass(admm_plan* plan, admm_state* st, int node0, int nodes, int with
 /* launches issued by this library since load (the bench's gpu_launches evidence) */
 long long admm_launch_count(void);
 
+/* optional CUDA-event profiler: one event pair per launch on the launching stream, summed per kernel class:
+ * 0 fwd, 1 fwd_reduce, 2 back_plain, 3 back_hp, 4 back_resid0, 5 colnorm2, 6 tv, 7 cg_update, 8 p_update,
+ * 9 sino_axpy, 10 sino_resid, 11 rhs0, 12 edge, 13 pack, 14 finalize, 15 fwd_fused(p-update) */
+#define ADMM_KC_COUNT 16
+int admm_profile_enable(int on);
+int admm_profile_read(double* ms, long long* cnt);
+
 #ifdef __cplusplus
 }
 #endif
