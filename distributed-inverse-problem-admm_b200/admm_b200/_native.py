@@ -14,7 +14,7 @@ _ROOT = os.path.dirname(_PKG)                      # distributed-inverse-problem
 CSRC = os.path.join(_ROOT, "csrc")
 LIB_PATH = os.path.join(_ROOT, "libadmm_b200.so")
 HEADER = os.path.join(os.path.dirname(_ROOT), "include", "admm_b200.h")
-SOURCES = ["api.cu", "projector.cu", "solver_kernels.cu"]
+SOURCES = ["api.cu", "projector.cu", "solver_kernels.cu", "tv_helpers.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -89,9 +89,12 @@ def lib():
     L.admm_edge_update.argtypes = [vp, ctypes.POINTER(State), vp, i, vp, vp]
     L.admm_pack.argtypes = [vp, vp, i, vp]
     L.admm_finalize.argtypes = [vp, ctypes.POINTER(State), vp, vp, vp, vp, i, vp, i, vp, vp]
+    L.admm_grad2d_host.argtypes = [i, vp, vp, vp]
+    L.admm_div2d_host.argtypes = [i, vp, vp, i, vp]
+    L.admm_kt_subgrad_host.argtypes = [i, vp, d, i, vp, vp]
     L.admm_profile_enable.argtypes = [i]
     L.admm_profile_read.argtypes = [vp, vp]
-    for name in ("admm_profile_enable", "admm_profile_read", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host", "admm_adjoint_host",
+    for name in ("admm_grad2d_host", "admm_div2d_host", "admm_kt_subgrad_host", "admm_profile_enable", "admm_profile_read", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host", "admm_adjoint_host",
                  "admm_rhs0", "admm_x_update", "admm_tv_pass", "admm_edge_update", "admm_pack", "admm_finalize"):
         getattr(L, name).restype = i
     _lib = L
@@ -101,7 +104,8 @@ def lib():
 EXPORTS = ("admm_version", "admm_last_error", "admm_device_count", "admm_plan_create", "admm_plan_destroy",
            "admm_plan_info", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host",
            "admm_adjoint_host", "admm_rhs0", "admm_x_update", "admm_edge_update", "admm_pack", "admm_finalize",
-           "admm_tv_pass", "admm_launch_count", "admm_profile_enable", "admm_profile_read")
+           "admm_tv_pass", "admm_launch_count", "admm_profile_enable", "admm_profile_read", "admm_grad2d_host",
+           "admm_div2d_host", "admm_kt_subgrad_host")
 
 KC_NAMES = ("fwd", "fwd_reduce", "back_plain", "back_hp", "back_resid0", "colnorm2", "tv", "cg_update", "p_update",
             "sino_axpy", "sino_resid", "rhs0", "edge", "pack", "finalize", "fwd_fused")

@@ -345,3 +345,84 @@ def solve(engine: ADMMEngine, max_iters, eps_pri, eps_dual, verbose=False, stop=
         if snapshot is not None:
             snapshot(k, engine)
     return done
+
+
+class NodeProblem:
+    """One node's subproblem, eq. (1) (block_5_node_problem.py:21-29), on the GPU:
+        min_x 1/2 |A x - b|^2 + lam TV(x) + rho/2 sum_j |x - v_j|^2_{Q_j}
+    solved by TV-split sweeps + CG through the same C-ABI x-update the outer loop uses (a graph with one node)."""
+
+    def __init__(self, op, b, rho, neighbor_terms, N, lam_tv, Qij_terms, tv_mu=None, device=None, prec=1.0):
+        torch = _torch()
+        nat.require_cuda()
+        if not hasattr(op, "angles"):
+            raise TypeError("Ai must be a matrix-free RayTransformCUDA operator (no dense / CPU path)")
+        device = op.device if device is None else device
+        self.torch, self.dev = torch, torch.device(f"cuda:{device}")
+        torch.cuda.set_device(self.dev)
+        self.N, self.n, self.D = int(N), int(N) * int(N), op.D
+        self.rho, self.lam = float(rho), float(lam_tv)
+        self.mu = float(tv_mu) if tv_mu is not None else (self.rho if self.rho > 0 else 1.0)
+        self.plan = Plan(N, [op.angles], op.D, op.det_w, device)
+        n, f32 = self.n, dict(dtype=torch.float32, device=self.dev)
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))).to(self.dev)  # noqa: E731
+        self.b = up(b).reshape(self.plan.A, self.D)
+        self.prec = torch.tensor([float(prec)], **f32)
+        self.atb = torch.empty(1, n, **f32)
+        self.plan.adjoint(self.b, self.atb, prec=self.prec)
+        deg = len(neighbor_terms)
+        if len(Qij_terms) != deg:
+            raise ValueError("neighbor_terms and Qij_terms must have the same length")
+        self.v = torch.stack([up(v) for v in neighbor_terms]) if deg else torch.zeros(1, n, **f32)
+        self.qv = torch.stack([up(q) for q in Qij_terms]) if deg else torch.zeros(1, n, **f32)
+        self.zero = torch.zeros(n, **f32)
+        self.deg = deg
+        z = lambda *s: torch.zeros(*s, **f32)  # noqa: E731
+        self.x, self.r, self.p0, self.p1, self.hp = z(1, n), z(1, n), z(1, n), z(1, n), z(1, n)
+        self.rhs0, self.tvterm = z(1, n), z(1, n)
+        self.w0, self.w1 = z(1, 2, n), z(1, 2, n)
+        self.q, self.ax = z(self.plan.A, self.D), z(self.plan.A, self.D)
+        self.scal = torch.zeros(1, nat.NSCAL, dtype=torch.float64, device=self.dev)
+        self.part = z(self.plan.part_floats)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.rhoD_vec = (self.rho * self.qv[:deg].sum(dim=0)).reshape(1, n).contiguous() if deg else z(1, n)
+        self.rhoD_s = z(1)
+        st = self.st = nat.State()
+        for name in ("x", "r", "p0", "p1", "hp", "rhs0", "tvterm", "atb", "w0", "w1", "q", "ax", "b", "scal", "part",
+                     "counter", "rhoD_s", "rhoD_vec", "prec"):
+            setattr(st, name, getattr(self, name).data_ptr())
+        st.xtrue = None
+        st.stride, st.rho, st.lam, st.mu, st.q_uniform = n, self.rho, self.lam, self.mu, 1.0
+        st.w_parity, st.fuse_pupdate = 0, 1
+        ptr = torch.tensor([0, deg], dtype=torch.int32, device=self.dev)
+        a = lambda t, k: t.data_ptr() + k * n * 4  # noqa: E731
+        i64 = lambda v: torch.tensor(v if v else [0], dtype=torch.int64, device=self.dev)  # noqa: E731
+        self._tabs = (ptr, i64([a(self.v, k) for k in range(deg)]), i64([self.zero.data_ptr()] * deg),
+                      i64([a(self.qv, k) for k in range(deg)]))
+        s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        nat.check(nat.lib().admm_rhs0(self.plan.handle, ctypes.byref(st), ptr.data_ptr(), self._tabs[1].data_ptr(),
+                                      self._tabs[2].data_ptr(), self._tabs[3].data_ptr(), 0, 1, s), "admm_rhs0")
+        self.cg_done = 0
+
+    def sweep(self, cg_iters, sweeps=1):
+        s = ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+        nat.check(nat.lib().admm_x_update(self.plan.handle, ctypes.byref(self.st), 0, 1, sweeps, cg_iters, s),
+                  "admm_x_update")
+        self.st.w_parity ^= (sweeps & 1)
+        self.cg_done += sweeps * cg_iters
+
+    def stats(self):
+        """(objective of eq. (1) with canonical TV, stationarity norm |g|) of the current x."""
+        sc = self.scal[0].cpu().numpy()
+        x = self.x[0]
+        pen = 0.0
+        if self.deg:
+            pen = float(((x[None, :] - self.v[: self.deg]) ** 2 * self.qv[: self.deg]).sum().item())
+        obj = 0.5 * float(self.prec.item()) * sc[nat.S_MSE] + self.lam * sc[nat.S_TV] + 0.5 * self.rho * pen
+        return obj, math.sqrt(max(sc[nat.S_GN2], 0.0))
+
+    def x_value(self):
+        return self.x[0].cpu().numpy().astype(np.float64)
+
+    def close(self):
+        self.plan.close()

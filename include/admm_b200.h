@@ -140,6 +140,16 @@ int admm_finalize(admm_plan* plan, const admm_state* st, const double* d_sums, c
  * used by the drop-in block_4 module; outputs w', tvterm' and TV(x) like the fused K3. */
 int admm_tv_pass(admm_plan* plan, admm_state* st, int node0, int nodes, int with_diag, void* stream);
 
+/* ---- block_4 NumPy helpers on device, HOST fp64 buffers (bit-identical to the reference's float64 NumPy) ----
+ * admm_grad2d_host     : _grad_forward_2d_from_vec        block_4_tv_helpers.py:17-23
+ * admm_div2d_host      : _div_backward_2d_to_vec          block_4_tv_helpers.py:25-35 (exact_adjoint=0: as shipped,
+ *                        border rows/columns sign-flipped; 1: the exact K^T the solver uses)
+ * admm_kt_subgrad_host : kt_subgrad_isotropic_tv_from_x   block_4_tv_helpers.py:37-46; h_mag (optional) receives
+ *                        |grad x| = edge_map_from_vector  block_4_tv_helpers_with_plot.py:23-46 */
+int admm_grad2d_host(int N, const double* h_x, double* h_gx, double* h_gy);
+int admm_div2d_host(int N, const double* h_px, const double* h_py, int exact_adjoint, double* h_out);
+int admm_kt_subgrad_host(int N, const double* h_x, double eps, int exact_adjoint, double* h_out, double* h_mag);
+
 /* launches issued by this library since load (the bench's gpu_launches evidence) */
 long long admm_launch_count(void);
 

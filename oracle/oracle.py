@@ -394,9 +394,10 @@ def tv_reference_pairing(x_vec, N):
 # Precisions and graphs (a7, a8)
 # ----------------------------------------------------------------------------------------------
 def make_precisions(Wi_raw, q_mode="arithmetic"):
-    """block_3_graph_and_precisions.py:11-43 with W_i supplied as column norms^2."""
+    """block_3_graph_and_precisions.py:11-43 with W_i supplied as column norms^2 (dtype preserved: the reference's
+    W, Q are float32 when A is)."""
     eps = 1e-12
-    Wi_list = [np.maximum(np.asarray(w, dtype=np.float64), eps) for w in Wi_raw]
+    Wi_list = [np.maximum(np.asarray(w), eps) for w in Wi_raw]
     if q_mode == "harmonic":
         def Q(i, j):
             return np.maximum(Wi_list[i] * Wi_list[j] / (Wi_list[i] + Wi_list[j]), eps)
