@@ -80,7 +80,7 @@ struct admm_plan {
     int* d_anode = nullptr;          // [A]
     float* d_recs = nullptr;         // [A][nRec][span]
     int* d_jstart = nullptr;         // [A][nRec]
-    int nTi = 0, nSeg = 0, span = 0, bspan = 0, max_chunks = 1;
+    int nTi = 0, nSeg = 0, span = 0, bspan = 0, max_chunks = 1, seg = FSEG_MAX;
     long long ws_bytes = 0;
     // scratch of the host-buffer entry points
     float* d_himg = nullptr;
@@ -112,7 +112,7 @@ static void build_angle_rec(int N, int D, double det_w, float c32, float s32, An
     r->wgt = (float)(h / std::fabs(xdom ? c : s));
     r->inv_om = (float)(1.0 / std::fabs(M));
     r->xdom = xdom ? 1 : 0;
-    r->pad = 0;
+    r->inv_slope = (std::fabs(m / M) > 1e-6) ? (float)(M / m) : 0.0f;
 }
 
 extern "C" admm_plan* admm_plan_create(int N, int D, double det_w, int V, const int* ang_ptr, const float* cos32,
@@ -137,7 +137,16 @@ extern "C" admm_plan* admm_plan_create(int N, int D, double det_w, int V, const 
     p->recs_h.resize(A > 0 ? A : 1);
     std::vector<int> optr(2 * (V + 1), 0), oidx(A > 0 ? A : 1, 0), anode(A > 0 ? A : 1, 0);
     double ext_f = 0.0, ext_b = 0.0;
-    const int Wm = std::min(FW, N), Km = std::min(FSEG, N);
+    p->nTi = (N + FW - 1) / FW;
+    {   // segment length: as long as possible (fewer records) while the grid still fills the GPU several times
+        const long long want_blocks = 148LL * 6;
+        long long nseg = (want_blocks + (long long)V * p->nTi - 1) / ((long long)V * p->nTi);
+        const long long max_seg_count = (N + FL - 1) / FL;
+        nseg = std::max(1LL, std::min(nseg, max_seg_count));
+        int seg = (int)(((N + nseg - 1) / nseg + FL - 1) / FL) * FL;
+        p->seg = std::max(FL, std::min(seg, FSEG_MAX));
+    }
+    const int Wm = std::min(FW, N), Km = std::min(p->seg, N);
     for (int a = 0; a < A; ++a) {
         build_angle_rec(N, D, det_w, cos32[a], sin32[a], &p->recs_h[a]);
         const AngleRec& r = p->recs_h[a];
@@ -147,8 +156,7 @@ extern "C" admm_plan* admm_plan_create(int N, int D, double det_w, int V, const 
     }
     p->span = (int)std::ceil(ext_f) + 4;
     p->bspan = (int)std::ceil(ext_b) + 6;
-    p->nTi = (N + FW - 1) / FW;
-    p->nSeg = (N + FSEG - 1) / FSEG;
+    p->nSeg = (N + p->seg - 1) / p->seg;
     // orientation lists: [x-dominant angles of node 0..V-1][y-dominant angles of node 0..V-1]
     int pos = 0;
     p->max_chunks = 1;
@@ -208,8 +216,9 @@ extern "C" long long admm_plan_info(const admm_plan* p, int what) {
         case ADMM_INFO_V: return p->V;
         case ADMM_INFO_A: return p->A;
         case ADMM_INFO_PART_FLOATS: {
-            const long long tiles = (long long)((p->N + 31) / 32) * ((p->N + 31) / 32);
-            return std::max(3 * tiles, 5LL * 4096);
+            const long long tiles = (long long)((p->N + 31) / 32) * ((p->N + 31) / 32);       // back-projector grid
+            const long long tvblk = (long long)((p->N + 127) / 128) * ((p->N + 7) / 8);       // TV grid
+            return std::max(std::max(3 * tiles, 3 * tvblk), 5LL * 4096);
         }
         case ADMM_INFO_FWD_SPAN: return p->span;
         case ADMM_INFO_FWD_NREC: return (long long)p->nTi * p->nSeg;
@@ -229,7 +238,7 @@ static FwdParams make_fwd(const admm_plan* p, const float* img, long long stride
     FwdParams P{};
     P.img = img; P.img_stride = stride; P.ang = p->d_ang; P.optr = p->d_optr; P.oidx = p->d_oidx;
     P.recs = p->d_recs; P.jstart = p->d_jstart; P.V = p->V; P.node0 = node0; P.N = p->N; P.D = p->D;
-    P.nTi = p->nTi; P.nSeg = p->nSeg; P.span = p->span;
+    P.nTi = p->nTi; P.nSeg = p->nSeg; P.span = p->span; P.seg = p->seg;
     P.r = nullptr; P.p_out = nullptr; P.scal = nullptr; P.beta_num = 0; P.beta_den = 0;
     return P;
 }

@@ -32,7 +32,7 @@ struct AngleRec {
     float wgt;        // h / |a|, a = xdom ? cos : sin   (Joseph step length)
     float inv_om;     // 1 / |major| = 1 / omega  (hat half-width in bins is omega)
     int xdom;         // 1: |cos| > |sin| -> step along iy, interpolate along ix
-    int pad;
+    float inv_slope;  // major / minor, 0 when |slope| <= 1e-6 (ray parallel to the step axis)
 };
 static_assert(sizeof(AngleRec) == 40, "AngleRec layout is part of the C ABI");
 
@@ -45,10 +45,11 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Block-wide sum of K floats per thread; result valid in thread 0.  red must hold K * 32 floats.
+// Block-wide sum of K floats per thread (1-D or 2-D blocks); result valid in linear thread 0.  red: K * 32 floats.
 template <int K>
 __device__ __forceinline__ void block_sum(float (&v)[K], float* red) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5, nw = (blockDim.x * blockDim.y + 31) >> 5;
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
     __syncthreads();
@@ -75,7 +76,8 @@ template <int K>
 __device__ __forceinline__ void grid_reduce_store(const float (&v)[K], float* part, unsigned* counter,
                                                   int blk, int nblk, double* out, float* red) {
     __shared__ int s_last;
-    if (threadIdx.x == 0) {
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < K; ++k) part[(size_t)blk * K + k] = v[k];
         __threadfence();
@@ -89,12 +91,12 @@ __device__ __forceinline__ void grid_reduce_store(const float (&v)[K], float* pa
         double acc[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[k] = 0.0;
-        for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+        for (int b = tid; b < nblk; b += nthr) {
 #pragma unroll
             for (int k = 0; k < K; ++k) acc[k] += (double)__ldcg(&part[(size_t)b * K + k]);
         }
         double* dred = reinterpret_cast<double*>(red);  // red holds >= 32*K floats -> reuse per k
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        const int lane = tid & 31, wid = tid >> 5, nw = (nthr + 31) >> 5;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             double a = acc[k];
@@ -103,15 +105,35 @@ __device__ __forceinline__ void grid_reduce_store(const float (&v)[K], float* pa
             __syncthreads();
             if (lane == 0) dred[wid] = a;
             __syncthreads();
-            if (threadIdx.x == 0) {
+            if (tid == 0) {
                 double s = 0.0;
                 for (int w = 0; w < nw; ++w) s += dred[w];
                 out[k] = s;
             }
         }
-        if (threadIdx.x == 0) *counter = 0u;
+        if (tid == 0) *counter = 0u;
     }
 }
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f32_4(unsigned addr) {  // [addr + 4]
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// both taps of a linear interpolation through ONE address register: a = [addr], b = [addr + 4]
+__device__ __forceinline__ void lds_pair(unsigned addr, float& a, float& b) {
+    asm volatile("ld.shared.f32 %0, [%2];\n\tld.shared.f32 %1, [%2+4];" : "=f"(a), "=f"(b) : "r"(addr));
+}
+// make a value opaque to the optimiser (stops it from re-deriving / re-associating loop invariants per use)
+__device__ __forceinline__ void opaque(unsigned& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void opaque(float& v) { asm volatile("" : "+f"(v)); }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }

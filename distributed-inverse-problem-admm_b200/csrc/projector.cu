@@ -18,7 +18,7 @@ namespace admm {
 // per slab -> no atomics).  At the end the rows are stored as fixed-size records; fwd_reduce_kernel sums
 // the records of all strips/segments in a fixed order (deterministic) and applies the step weight.
 // =================================================================================================
-__global__ void __launch_bounds__(FTHREADS)
+__global__ void __launch_bounds__(FTHREADS, 4)
 fwd_strip_kernel(const FwdParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* S = reinterpret_cast<float*>(smem_raw);                 // [FL][FPITCH]
@@ -26,6 +26,8 @@ fwd_strip_kernel(const FwdParams P) {
     double* s_base = reinterpret_cast<double*>(acc_s + FAC * P.span + ((FAC * P.span) & 1));  // [FAC]
     int* s_jseg = reinterpret_cast<int*>(s_base + FAC);            // [FAC]
     int* s_aid = s_jseg + FAC;                                     // [FAC]
+    int4* s_win = reinterpret_cast<int4*>(s_aid + FAC);            // [FAC] per slab: jmin, jmax, jb, fb(bits)
+    float4* s_ang = reinterpret_cast<float4*>(s_win + FAC);        // [FAC] inv_major, slope, inv_slope, -
 
     const int node = P.node0 + blockIdx.y;
     const int orient = blockIdx.z;  // 0: x-dominant list, 1: y-dominant list
@@ -40,21 +42,24 @@ fwd_strip_kernel(const FwdParams P) {
 
     const float* __restrict__ img = P.img + (long long)blockIdx.y * P.img_stride;
     const int U0 = ti * FW, Wt = min(FW, N - U0);
-    const int K0seg = sg * FSEG, Kseg = min(FSEG, N - K0seg);
+    const int K0seg = sg * P.seg, Kseg = min(P.seg, N - K0seg);
     const int tid = threadIdx.x;
     const double cx = 0.5 * (N - 1), cj = 0.5 * (D - 1);
 
     for (int i = tid; i < FAC * span; i += FTHREADS) acc_s[i] = 0.f;
+    double my_M = 0.0, my_m = 0.0;   // threads < na keep their angle's (major, minor) tau steps
     if (tid < na) {
         const int aid = P.oidx[a0 + tid];
         const AngleRec r = P.ang[aid];
-        const double M = xdom ? r.ct : r.st, m = xdom ? r.st : r.ct;
-        const double base = cj + (U0 - cx) * M + (K0seg - cx) * m;  // tau of pixel (u=0,k=0) of the segment
-        const double e1 = (Wt - 1) * M, e2 = (Kseg - 1) * m;
+        my_M = xdom ? r.ct : r.st;
+        my_m = xdom ? r.st : r.ct;
+        const double base = cj + (U0 - cx) * my_M + (K0seg - cx) * my_m;  // tau of pixel (u=0,k=0) of the segment
+        const double e1 = (Wt - 1) * my_M, e2 = (Kseg - 1) * my_m;
         const double lo = base + fmin(e1, 0.0) + fmin(e2, 0.0);
         s_base[tid] = base;
-        s_jseg[tid] = (int)ceil(lo - fabs(M)) - 1;   // one bin of slack below the exact bound
+        s_jseg[tid] = (int)ceil(lo - fabs(my_M)) - 1;   // one bin of slack below the exact bound
         s_aid[tid] = aid;
+        s_ang[tid] = make_float4(r.inv_major, r.slope, r.inv_slope, 0.f);
     }
 
     // fused CG direction update p_new = r + beta p_old
@@ -74,9 +79,21 @@ fwd_strip_kernel(const FwdParams P) {
 
     const int slot = tid / FTPA, t = tid % FTPA;
     const int nslab = (Kseg + FL - 1) / FL;
+    // shared-window byte address of S[0][-1+1] minus the magic-number bias: addr(k, i) = sbase + k*pitch*4 + bits(i)*4
+    const unsigned sbase = smem_u32(S) + 4u - ((unsigned)kMagicBits << 2);
     for (int slab = 0; slab < nslab; ++slab) {
         const int K0 = K0seg + slab * FL, Lt = min(FL, K0seg + Kseg - K0);
         __syncthreads();  // previous slab fully consumed (also orders the acc/zero + setup writes)
+        // ---- per-angle detector window of this slab (one thread per angle) ------------------------------
+        if (tid < na) {
+            const double base = s_base[tid] + (double)(slab * FL) * my_m;  // tau of slab pixel (0,0)
+            const double e1 = (Wt - 1) * my_M, e2 = (Lt - 1) * my_m, om = fabs(my_M);
+            const double tlo = base + fmin(e1, 0.0) + fmin(e2, 0.0) - om;
+            const double thi = base + fmax(e1, 0.0) + fmax(e2, 0.0) + om;
+            const double fbase = floor(base);
+            s_win[tid] = make_int4(max(0, (int)ceil(tlo)), min(D - 1, (int)floor(thi)), (int)fbase,
+                                   __float_as_int((float)(base - fbase)));
+        }
         // ---- stage tile -------------------------------------------------------------------------
         if (xdom) {
             // pixel (ix = U0+u, iy = K0+k): contiguous along k.  thread -> (u, 4 consecutive k)
@@ -128,52 +145,57 @@ fwd_strip_kernel(const FwdParams P) {
         __syncthreads();
         // ---- sample ---------------------------------------------------------------------------------
         for (int ai = slot; ai < na; ai += FTHREADS / FTPA) {
-            const AngleRec r = P.ang[s_aid[ai]];
-            const double M = xdom ? r.ct : r.st, m = xdom ? r.st : r.ct;
-            const double base = s_base[ai] + (double)(slab * FL) * m;  // tau of slab pixel (0,0)
-            const double e1 = (Wt - 1) * M, e2 = (Lt - 1) * m, om = fabs(M);
-            const double tlo = base + fmin(e1, 0.0) + fmin(e2, 0.0) - om;
-            const double thi = base + fmax(e1, 0.0) + fmax(e2, 0.0) + om;
-            const int jmin = max(0, (int)ceil(tlo)), jmax = min(D - 1, (int)floor(thi));
-            const double fbase = floor(base);
-            const int jb = (int)fbase;
-            const float fb = (float)(base - fbase);
-            const float s = r.slope, im = r.inv_major;
-            const float vlo = -1.5f, vhi = (float)Wt - 0.5f;
+            const int4 win = s_win[ai];
+            const float4 ar = s_ang[ai];
+            const float fb = __int_as_float(win.w);
+            const float im = ar.x, s = ar.y, rs = ar.z;
+            const float ulo = -1.0f, uhi = (float)Wt;
             const int jseg = s_jseg[ai];
-            for (int j = jmin + t; j <= jmax; j += FTPA) {
-                const float v0 = ((float)(j - jb) - fb) * im - 0.5f;  // v_k = v0 - k s,  u = v + 0.5
+            for (int j = win.x + t; j <= win.y; j += FTPA) {
+                const float u0 = ((float)(j - win.z) - fb) * im;   // u_k = u0 - k s  (interp-axis pixel coordinate)
                 int klo = 0, khi = Lt - 1;
-                if (fabsf(s) > 1e-6f) {
-                    const float rs = 1.0f / s;
-                    const float ka = (v0 - vhi) * rs, kb = (v0 - vlo) * rs;
-                    const float kmn = fminf(ka, kb), kmx = fmaxf(ka, kb);
-                    klo = max(0, (int)fmaxf(ceilf(kmn) - 1.f, -1.f));
-                    khi = min(Lt - 1, (int)fminf(floorf(kmx) + 1.f, (float)FL));
+                if (rs != 0.f) {
+                    const float ka = (u0 - uhi) * rs, kb = (u0 - ulo) * rs;
+                    klo = max(0, (int)fmaxf(ceilf(fminf(ka, kb)) - 1.f, -1.f));
+                    khi = min(Lt - 1, (int)fminf(floorf(fmaxf(ka, kb)) + 1.f, (float)FL));
                 }
                 while (klo <= khi) {
-                    const float v = fmaf(-(float)klo, s, v0);
-                    if (v > vlo && v <= vhi) break;
+                    const float u = fmaf(-(float)klo, s, u0);
+                    if (u >= ulo && u <= uhi) break;
                     ++klo;
                 }
                 while (klo <= khi) {
-                    const float v = fmaf(-(float)khi, s, v0);
-                    if (v > vlo && v <= vhi) break;
+                    const float u = fmaf(-(float)khi, s, u0);
+                    if (u >= ulo && u <= uhi) break;
                     --khi;
                 }
                 float acc = 0.f;
                 float kf = (float)klo;
-                const float* row = S + klo * FPITCH + 1;
-                for (int k = klo; k <= khi; ++k) {
-                    const float v = fmaf(-kf, s, v0);
-                    const float fi = v + kMagic;
-                    const int ii = __float_as_int(fi) - kMagicBits;
-                    const float f = (v - (fi - kMagic)) + 0.5f;
-                    const float a = row[ii], b = row[ii + 1];
-                    acc += fmaf(f, b - a, a);
-                    kf += 1.f;
-                    row += FPITCH;
+                unsigned rowa = sbase + (unsigned)(klo * FPITCH * 4);
+                int k = klo;
+#define FWD_SAMPLE(UU, ROWOFF)                                                              \
+    {                                                                                       \
+        const float fi = __fadd_rd((UU), kMagic);            /* floor(u) + magic, exact */ \
+        const float f = (UU) - (fi - kMagic);                /* in [0, 1) */               \
+        const unsigned addr = (__float_as_uint(fi) << 2) + rowa + (ROWOFF);                 \
+        float a, b;                                                                         \
+        lds_pair(addr, a, b);                                                               \
+        acc += fmaf(f, b - a, a);                                                           \
+    }
+                for (; k + 7 <= khi; k += 8) {
+                    const float ub = fmaf(-kf, s, u0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) FWD_SAMPLE(fmaf(-(float)q, s, ub), (unsigned)(q * FPITCH * 4))
+                    kf += 8.f;
+                    rowa += 8 * FPITCH * 4;
                 }
+                for (; k <= khi; ++k) {
+                    const float u = fmaf(-kf, s, u0);
+                    FWD_SAMPLE(u, 0u)
+                    kf += 1.f;
+                    rowa += FPITCH * 4;
+                }
+#undef FWD_SAMPLE
                 const int idx = j - jseg;
                 if (idx >= 0 && idx < span) acc_s[ai * span + idx] += acc;
             }
@@ -217,6 +239,7 @@ back_tile_kernel(const BackParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* qs = reinterpret_cast<float*>(smem_raw);       // [BAC][bspan]
     float4* s_c = reinterpret_cast<float4*>(qs + BAC * P.bspan + ((4 - ((BAC * P.bspan) & 3)) & 3));  // [BAC]
+    unsigned* s_qa = reinterpret_cast<unsigned*>(s_c + BAC);  // [BAC] biased shared-window address of each window
     __shared__ float red[64];
 
     const int node = P.node0 + blockIdx.z;
@@ -230,6 +253,9 @@ back_tile_kernel(const BackParams P) {
     const float prec = (MODE == BACK_COLNORM2 || P.prec == nullptr) ? 1.f : P.prec[node];
 
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float fx = (float)lx, fy = (float)ly;
+    opaque(fx);
+    opaque(fy);
     for (int c0 = abeg; c0 < aend; c0 += BAC) {
         const int na = min(BAC, aend - c0);
         __syncthreads();
@@ -247,32 +273,38 @@ back_tile_kernel(const BackParams P) {
                 if (j >= 0 && j < D) val = (MODE == BACK_COLNORM2) ? sc : sc * P.q[(long long)(c0 + ai) * D + j];
                 qs[ai * bspan + k] = val;
             }
-            if ((tid & 31) == 0)
-                s_c[ai] = make_float4((float)(tau0 - (double)jw0), (float)r.ct, (float)r.st, r.inv_om);
+            if ((tid & 31) == 0) {  // window-relative tau of pixel (0,0), pre-biased by -1/2 for the rint trick
+                s_c[ai] = make_float4((float)(tau0 - (double)jw0 - 0.5), (float)r.ct, (float)r.st, r.inv_om);
+                // read back through shared memory so the magic-number bias stays folded into ONE register
+                s_qa[ai] = smem_u32(qs) + (unsigned)(ai * bspan * 4) - ((unsigned)kMagicBits << 2);
+            }
         }
         __syncthreads();
         for (int ai = 0; ai < na; ++ai) {
             const float4 c = s_c[ai];
-            const float* __restrict__ qa = qs + ai * bspan;
             const float a = c.w;  // 1/omega
-            const float tb = fmaf((float)lx, c.y, fmaf((float)ly, c.z, c.x));
+            const float tb = fmaf(fx, c.y, fmaf(fy, c.z, c.x));   // tau - 1/2 of this thread's first pixel
             if (a >= 1.0f) {
-                const float c1 = 1.f - 0.5f * a;
+                const float c1 = fmaf(-0.5f, a, 1.f);
+                const unsigned qa = s_qa[ai];
 #pragma unroll
                 for (int px = 0; px < 4; ++px) {
-                    const float v = fmaf((float)px, c.z, tb) - 0.5f;
+                    const float v = (px == 0) ? tb : fmaf((float)px, c.z, tb);
                     const float fi = v + kMagic;
-                    const int j0 = __float_as_int(fi) - kMagicBits;
-                    const float up = v - (fi - kMagic);
+                    const float up = v - (fi - kMagic);               // in [-1/2, 1/2]
+                    const unsigned addr = (__float_as_uint(fi) << 2) + qa;
+                    float q0, q1;
+                    lds_pair(addr, q0, q1);
                     float w0 = fmaxf(0.f, fmaf(-a, up, c1)), w1 = fmaxf(0.f, fmaf(a, up, c1));
                     if (MODE == BACK_COLNORM2) { w0 *= w0; w1 *= w1; }
-                    acc[px] = fmaf(w0, qa[j0], fmaf(w1, qa[j0 + 1], acc[px]));
+                    acc[px] = fmaf(w0, q0, fmaf(w1, q1, acc[px]));
                 }
             } else {
+                const float* __restrict__ qa = qs + ai * bspan;
                 const float om = 1.f / a;
 #pragma unroll
                 for (int px = 0; px < 4; ++px) {
-                    const float tau = fmaf((float)px, c.z, tb);
+                    const float tau = fmaf((float)px, c.z, tb) + 0.5f;
                     const int jlo = (int)ceilf(tau - om), jhi = (int)floorf(tau + om);
                     for (int j = max(jlo, 0); j <= min(jhi, bspan - 1); ++j) {
                         float w = fmaxf(0.f, 1.f - fabsf(tau - (float)j) * a);
@@ -358,7 +390,7 @@ back_tile_kernel(const BackParams P) {
 static size_t fwd_smem_bytes(int span) {
     size_t f = (size_t)FL * FPITCH + (size_t)FAC * span;
     f += (f & 1);
-    return f * sizeof(float) + FAC * sizeof(double) + 2 * FAC * sizeof(int);
+    return f * sizeof(float) + FAC * sizeof(double) + 2 * FAC * sizeof(int) + FAC * sizeof(int4) + FAC * sizeof(float4);
 }
 
 cudaError_t launch_forward(const FwdParams& P, int nodes, int max_chunks, const FwdReduceParams& R,
@@ -381,7 +413,7 @@ cudaError_t launch_forward(const FwdParams& P, int nodes, int max_chunks, const 
 cudaError_t launch_back(int mode, const BackParams& P, int nodes, cudaStream_t st) {
     size_t f = (size_t)BAC * P.bspan;
     f += (4 - (f & 3)) & 3;
-    const size_t smem = f * sizeof(float) + BAC * sizeof(float4);
+    const size_t smem = f * sizeof(float) + BAC * sizeof(float4) + BAC * sizeof(unsigned);
     dim3 grid((P.N + BTY - 1) / BTY, (P.N + BTX - 1) / BTX, nodes);
     switch (mode) {
         case BACK_PLAIN: { ProfScope ps(KC_BACK_PLAIN, st); back_tile_kernel<BACK_PLAIN><<<grid, BTHREADS, smem, st>>>(P); } break;

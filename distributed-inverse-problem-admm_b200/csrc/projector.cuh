@@ -7,7 +7,7 @@ namespace admm {
 // ---- K1 forward: strip/segment decomposition ----------------------------------------------------
 constexpr int FW = 120;       // interpolation-axis extent of a strip (pixels)
 constexpr int FL = 32;        // steps per staged slab
-constexpr int FSEG = 256;     // steps per block segment (8 slabs)
+constexpr int FSEG_MAX = 256; // max steps per block segment (the plan picks seg <= FSEG_MAX, a multiple of FL)
 constexpr int FTPA = 128;     // threads per angle slot (bins handled per round)
 constexpr int FAC = 16;       // angles per block chunk
 constexpr int FTHREADS = 256; // 2 angle slots
@@ -24,7 +24,7 @@ struct FwdParams {
     int V;                   // nodes in optr tables
     int node0;               // first node of this launch
     int N, D;
-    int nTi, nSeg, span;
+    int nTi, nSeg, span, seg;  // seg = steps per segment
     // optional fused CG direction update p_new = r + beta * p_old (img = p_old)
     const float* r;          // [nodes][N*N] or nullptr
     float* p_out;            // [nodes][N*N]

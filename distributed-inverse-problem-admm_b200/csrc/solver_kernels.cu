@@ -12,95 +12,185 @@ namespace admm {
 // through the identity A^T P(Ax-b) + rho(Dx - sum q v) = tvterm - r_cg - mu K^T K x), and |x - x_true|^2
 // (:199-206).  Gradient = block_4_tv_helpers.py:17-23; div_ref = :25-35 as shipped (border sign quirk).
 // =================================================================================================
-constexpr int TT = 32;  // tile edge
+// Streaming form: block (32, 8) covers 8 rows x 128 columns, each thread owns 4 consecutive pixels of one row
+// (float4 loads / stores) and recomputes the (d - w') of its upper and left neighbours in registers, so there is
+// no shared-memory tile, no barrier before the reduction and every global access is a coalesced 16-byte one.
+constexpr int TVX = 32, TVY = 8;
 
-__global__ void __launch_bounds__(256)
+struct Dw { float dwx, dwy, w1, w2; };
+
+__device__ __forceinline__ Dw shrink_dw(float gx, float gy, float w1, float w2, float kappa) {
+    const float g1 = gx + w1, g2 = gy + w2;
+    const float n2 = fmaf(g1, g1, g2 * g2);
+    const float sc = (n2 > kappa * kappa) ? (1.f - kappa * rsqrtf(n2)) : 0.f;
+    const float d1 = sc * g1, d2 = sc * g2;
+    Dw o;
+    o.w1 = g1 - d1; o.w2 = g2 - d2;
+    o.dwx = d1 - o.w1; o.dwy = d2 - o.w2;
+    return o;
+}
+
+__device__ __forceinline__ void unit_grad(float gx, float gy, float& px, float& py, float& mag) {
+    const float n2 = fmaf(gx, gx, gy * gy);
+    if (n2 > 1e-24f) {
+        const float inv = rsqrtf(n2);
+        px = gx * inv; py = gy * inv; mag = n2 * inv;
+    } else { px = 0.f; py = 0.f; mag = 0.f; }
+}
+
+// guarded row-segment load: v[k] = row[c + k] for k in [0, CNT), zero outside [0, N)
+template <int CNT>
+__device__ __forceinline__ void load_seg(const float* __restrict__ row, int c, int N, bool rowok, bool vec, float* v) {
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) v[k] = 0.f;
+    if (!rowok) return;
+    // layout of every caller: element 1..4 are the aligned quad when CNT >= 5 and the segment starts at c0-1
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) {
+        const int cc = c + k;
+        if (cc >= 0 && cc < N) v[k] = row[cc];
+    }
+    (void)vec;
+}
+
+__global__ void __launch_bounds__(TVX * TVY)
 tv_fused_kernel(const TvParams P) {
-    __shared__ float xs[TT + 2][TT + 3];      // x rows R0-1..R0+32, cols C0-1..C0+32
-    __shared__ float dwx[TT + 1][TT + 2], dwy[TT + 1][TT + 2];  // (d - w') at rows R0-1..R0+31, cols C0-1..C0+31
-    __shared__ float pxs[TT + 1][TT + 2], pys[TT + 1][TT + 2];  // normalised gradient (diagnostic)
     __shared__ float red[96];
-    const int N = P.N, tid = threadIdx.x;
+    const int N = P.N;
     const int node = P.node0 + blockIdx.z;
     const long long nb = (long long)blockIdx.z * P.stride;
-    const int R0 = blockIdx.y * TT, C0 = blockIdx.x * TT;
-    const float* __restrict__ x = P.x + nb;
-    const float* __restrict__ win = P.w_in + 2 * nb;
-    float* __restrict__ wout = P.w_out + 2 * nb;
     const long long n = (long long)N * N;
+    const int r = blockIdx.y * TVY + threadIdx.y;
+    const int c0 = (blockIdx.x * TVX + threadIdx.x) * 4;
+    const float* __restrict__ x = P.x + nb;
+    const float* __restrict__ w1p = P.w_in + 2 * nb;
+    const float* __restrict__ w2p = w1p + n;
+    float* __restrict__ wo1 = P.w_out + 2 * nb;
+    float* __restrict__ wo2 = wo1 + n;
     const float kappa = P.lam / P.mu;
-
-    for (int i = tid; i < (TT + 2) * (TT + 2); i += 256) {
-        const int lr = i / (TT + 2), lc = i % (TT + 2);
-        const int r = R0 - 1 + lr, c = C0 - 1 + lc;
-        xs[lr][lc] = (r >= 0 && r < N && c >= 0 && c < N) ? x[(long long)r * N + c] : 0.f;
-    }
-    __syncthreads();
-    float tv = 0.f;
-    for (int i = tid; i < (TT + 1) * (TT + 1); i += 256) {
-        const int lr = i / (TT + 1), lc = i % (TT + 1);   // extended position (R0-1+lr, C0-1+lc)
-        const int r = R0 - 1 + lr, c = C0 - 1 + lc;
-        float ox = 0.f, oy = 0.f, nx = 0.f, ny = 0.f;
-        if (r >= 0 && r < N && c >= 0 && c < N) {
-            const float xc = xs[lr][lc];
-            const float gx0 = (r < N - 1) ? xs[lr + 1][lc] - xc : 0.f;
-            const float gy0 = (c < N - 1) ? xs[lr][lc + 1] - xc : 0.f;
-            const long long g = (long long)r * N + c;
-            const float g1 = gx0 + win[g], g2 = gy0 + win[n + g];
-            const float nrm = sqrtf(g1 * g1 + g2 * g2);
-            const float sc = (nrm > kappa) ? (1.f - kappa / nrm) : 0.f;
-            const float d1 = sc * g1, d2 = sc * g2;
-            const float w1 = g1 - d1, w2 = g2 - d2;
-            ox = d1 - w1;
-            oy = d2 - w2;
-            const float n0 = sqrtf(gx0 * gx0 + gy0 * gy0);
-            if (n0 > 1e-12f) { nx = gx0 / n0; ny = gy0 / n0; }
-            if (lr >= 1 && lc >= 1) {  // owned pixel
-                wout[g] = w1;
-                wout[n + g] = w2;
-                tv += n0;
+    float tv = 0.f, gn2 = 0.f, img = 0.f;
+    if (r < N && c0 < N) {
+        const bool vec = ((N & 3) == 0);   // then c0 + 3 < N and rows are 16-byte aligned
+        const long long g0 = (long long)r * N + c0;
+        float xm[5], xc[6], xp[5], wc1[5], wc2[5], wu1[4], wu2[4];
+        const bool up = r >= 1, dn = r + 1 < N;
+        if (vec) {
+            const float4 q = ld4(x + g0);
+            xc[1] = q.x; xc[2] = q.y; xc[3] = q.z; xc[4] = q.w;
+            xc[0] = (c0 >= 1) ? x[g0 - 1] : 0.f;
+            xc[5] = (c0 + 4 < N) ? x[g0 + 4] : 0.f;
+            if (up) {
+                const float4 a = ld4(x + g0 - N);
+                xm[0] = a.x; xm[1] = a.y; xm[2] = a.z; xm[3] = a.w;
+                xm[4] = (c0 + 4 < N) ? x[g0 - N + 4] : 0.f;
+                const float4 u1 = ld4(w1p + g0 - N), u2 = ld4(w2p + g0 - N);
+                wu1[0] = u1.x; wu1[1] = u1.y; wu1[2] = u1.z; wu1[3] = u1.w;
+                wu2[0] = u2.x; wu2[1] = u2.y; wu2[2] = u2.z; wu2[3] = u2.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) xm[k] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { wu1[k] = 0.f; wu2[k] = 0.f; }
+            }
+            if (dn) {
+                const float4 a = ld4(x + g0 + N);
+                xp[1] = a.x; xp[2] = a.y; xp[3] = a.z; xp[4] = a.w;
+                xp[0] = (c0 >= 1) ? x[g0 + N - 1] : 0.f;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) xp[k] = 0.f;
+            }
+            const float4 a1 = ld4(w1p + g0), a2 = ld4(w2p + g0);
+            wc1[1] = a1.x; wc1[2] = a1.y; wc1[3] = a1.z; wc1[4] = a1.w;
+            wc2[1] = a2.x; wc2[2] = a2.y; wc2[3] = a2.z; wc2[4] = a2.w;
+            wc1[0] = (c0 >= 1) ? w1p[g0 - 1] : 0.f;
+            wc2[0] = (c0 >= 1) ? w2p[g0 - 1] : 0.f;
+        } else {
+            load_seg<6>(x + (long long)r * N, c0 - 1, N, true, false, xc);
+            load_seg<5>(x + (long long)(r - 1) * N, c0, N, up, false, xm);
+            load_seg<5>(x + (long long)(r + 1) * N, c0 - 1, N, dn, false, xp);
+            load_seg<5>(w1p + (long long)r * N, c0 - 1, N, true, false, wc1);
+            load_seg<5>(w2p + (long long)r * N, c0 - 1, N, true, false, wc2);
+            load_seg<4>(w1p + (long long)(r - 1) * N, c0, N, up, false, wu1);
+            load_seg<4>(w2p + (long long)(r - 1) * N, c0, N, up, false, wu2);
+        }
+        // left neighbour (r, c0-1): only its y-component of (d - w') and of the unit gradient is needed
+        float dwy_prev = 0.f, py_prev = 0.f;
+        if (c0 >= 1) {
+            const float gx = dn ? xp[0] - xc[0] : 0.f, gy = xc[1] - xc[0];
+            dwy_prev = shrink_dw(gx, gy, wc1[0], wc2[0], kappa).dwy;
+            float pxl, mg;
+            unit_grad(gx, gy, pxl, py_prev, mg);
+        }
+        float w1o[4], w2o[4], tvo[4];
+        float told[4], rc[4], xt[4];
+        const bool diag = (P.r != nullptr);
+        float* __restrict__ tvt = P.tvterm + nb;
+        if (vec) {
+            const float4 t4 = ld4(tvt + g0);
+            told[0] = t4.x; told[1] = t4.y; told[2] = t4.z; told[3] = t4.w;
+            if (diag) { const float4 q = ld4(P.r + nb + g0); rc[0] = q.x; rc[1] = q.y; rc[2] = q.z; rc[3] = q.w; }
+            if (P.xtrue) { const float4 q = ld4(P.xtrue + g0); xt[0] = q.x; xt[1] = q.y; xt[2] = q.z; xt[3] = q.w; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool ok = c0 + k < N;
+                told[k] = ok ? tvt[g0 + k] : 0.f;
+                rc[k] = (ok && diag) ? P.r[nb + g0 + k] : 0.f;
+                xt[k] = (ok && P.xtrue) ? P.xtrue[g0 + k] : 0.f;
             }
         }
-        dwx[lr][lc] = ox; dwy[lr][lc] = oy; pxs[lr][lc] = nx; pys[lr][lc] = ny;
-    }
-    __syncthreads();
-    float gn2 = 0.f, img = 0.f;
-    const float* __restrict__ rcg = P.r ? P.r + nb : nullptr;
-    const float* __restrict__ xt = P.xtrue;
-    float* __restrict__ tvt = P.tvterm + nb;
-    for (int i = tid; i < TT * TT; i += 256) {
-        const int lr = i / TT + 1, lc = i % TT + 1;
-        const int r = R0 + lr - 1, c = C0 + lc - 1;
-        if (r >= N || c >= N) continue;
-        const long long g = (long long)r * N + c;
-        float kt = 0.f;
-        if (r >= 1) kt += dwx[lr - 1][lc];
-        if (r < N - 1) kt -= dwx[lr][lc];
-        if (c >= 1) kt += dwy[lr][lc - 1];
-        if (c < N - 1) kt -= dwy[lr][lc];
-        const float tv_old = tvt[g];
-        tvt[g] = P.mu * kt;
-        const float xc = xs[lr][lc];
-        if (rcg) {
-            float lap = 0.f;
-            if (r >= 1) lap += xc - xs[lr - 1][lc];
-            if (r < N - 1) lap += xc - xs[lr + 1][lc];
-            if (c >= 1) lap += xc - xs[lr][lc - 1];
-            if (c < N - 1) lap += xc - xs[lr][lc + 1];
-            // div_ref (block_4_tv_helpers.py:25-35): -div, sign-flipped border
-            float dv = 0.f;
-            if (N >= 2) {
-                if (r == 0) dv += pxs[lr][lc];
-                else if (r == N - 1) dv -= pxs[lr - 1][lc];
-                else dv += pxs[lr - 1][lc] - pxs[lr][lc];
-                if (c == 0) dv += pys[lr][lc];
-                else if (c == N - 1) dv -= pys[lr][lc - 1];
-                else dv += pys[lr][lc - 1] - pys[lr][lc];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + k;
+            const bool ok = c < N, rt = c + 1 < N, lf = c >= 1;
+            const float xcv = xc[k + 1];
+            const float gx = dn ? xp[k + 1] - xcv : 0.f;
+            const float gy = rt ? xc[k + 2] - xcv : 0.f;
+            const Dw o = shrink_dw(gx, gy, wc1[k + 1], wc2[k + 1], kappa);
+            float dwx_up = 0.f, px_up = 0.f;
+            if (up) {
+                const float gxu = xcv - xm[k], gyu = rt ? xm[k + 1] - xm[k] : 0.f;
+                dwx_up = shrink_dw(gxu, gyu, wu1[k], wu2[k], kappa).dwx;
+                float pyu, mg;
+                unit_grad(gxu, gyu, px_up, pyu, mg);
             }
-            const float gv = tv_old - rcg[g] - P.mu * lap + P.lam * dv;
-            gn2 = fmaf(gv, gv, gn2);
+            float kt = dwx_up;
+            if (dn) kt -= o.dwx;
+            if (lf) kt += dwy_prev;
+            if (rt) kt -= o.dwy;
+            float pxo, pyo, mag;
+            unit_grad(gx, gy, pxo, pyo, mag);
+            if (ok) {
+                tv += mag;
+                if (diag) {
+                    float lap = 0.f;
+                    if (up) lap += xcv - xm[k];
+                    if (dn) lap += xcv - xp[k + 1];
+                    if (lf) lap += xcv - xc[k];
+                    if (rt) lap += xcv - xc[k + 2];
+                    float dv = 0.f;   // block_4_tv_helpers.py:25-35 as shipped (-div, sign-flipped border)
+                    if (N >= 2) {
+                        if (r == 0) dv += pxo; else if (!dn) dv -= px_up; else dv += px_up - pxo;
+                        if (c == 0) dv += pyo; else if (!rt) dv -= py_prev; else dv += py_prev - pyo;
+                    }
+                    const float gv = told[k] - rc[k] - P.mu * lap + P.lam * dv;
+                    gn2 = fmaf(gv, gv, gn2);
+                }
+                if (P.xtrue) { const float e = xcv - xt[k]; img = fmaf(e, e, img); }
+            }
+            w1o[k] = o.w1; w2o[k] = o.w2; tvo[k] = P.mu * kt;
+            dwy_prev = o.dwy; py_prev = pyo;
         }
-        if (xt) { const float e = xc - xt[g]; img = fmaf(e, e, img); }
+        if (vec) {
+            st4(wo1 + g0, make_float4(w1o[0], w1o[1], w1o[2], w1o[3]));
+            st4(wo2 + g0, make_float4(w2o[0], w2o[1], w2o[2], w2o[3]));
+            st4(tvt + g0, make_float4(tvo[0], tvo[1], tvo[2], tvo[3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (c0 + k < N) { wo1[g0 + k] = w1o[k]; wo2[g0 + k] = w2o[k]; tvt[g0 + k] = tvo[k]; }
+        }
     }
     float v[3] = {tv, gn2, img};
     block_sum<3>(v, red);
@@ -158,7 +248,12 @@ p_update_kernel(const CgParams P) {
     const float* __restrict__ r = P.r + nb;
     const float* __restrict__ p = P.p + nb;
     float* __restrict__ po = P.p_out + nb;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += (long long)gridDim.x * blockDim.x)
+    const long long n4 = ((P.n & 3) == 0 && (P.stride & 3) == 0) ? (P.n >> 2) : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = ld4(p + 4 * i), b = ld4(r + 4 * i);
+        st4(po + 4 * i, make_float4(fmaf(beta, a.x, b.x), fmaf(beta, a.y, b.y), fmaf(beta, a.z, b.z), fmaf(beta, a.w, b.w)));
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += (long long)gridDim.x * blockDim.x)
         po[i] = fmaf(beta, p[i], r[i]);
 }
 
@@ -214,7 +309,22 @@ rhs0_kernel(const RhsParams P) {
     const int kb = P.nbr_ptr[node], ke = P.nbr_ptr[node + 1];
     const float* __restrict__ atb = P.atb + nb;
     float* __restrict__ out = P.rhs0 + nb;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += (long long)gridDim.x * blockDim.x) {
+    const long long n4 = ((P.n & 3) == 0 && (P.stride & 3) == 0) ? (P.n >> 2) : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 cons = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = kb; k < ke; ++k) {
+            const float4 z = ld4(reinterpret_cast<const float*>(P.nbr_z[k]) + 4 * i);
+            const float4 y = ld4(reinterpret_cast<const float*>(P.nbr_y[k]) + 4 * i);
+            const float* q = reinterpret_cast<const float*>(P.nbr_q[k]);
+            float4 qv = make_float4(P.q_uniform, P.q_uniform, P.q_uniform, P.q_uniform);
+            if (q) qv = ld4(q + 4 * i);
+            cons.x += P.rho * qv.x * (z.x - y.x); cons.y += P.rho * qv.y * (z.y - y.y);
+            cons.z += P.rho * qv.z * (z.z - y.z); cons.w += P.rho * qv.w * (z.w - y.w);
+        }
+        const float4 a = ld4(atb + 4 * i);
+        st4(out + 4 * i, make_float4(a.x + cons.x, a.y + cons.y, a.z + cons.z, a.w + cons.w));
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += (long long)gridDim.x * blockDim.x) {
         float cons = 0.f;
         for (int k = kb; k < ke; ++k) {
             const float* z = reinterpret_cast<const float*>(P.nbr_z[k]);
@@ -235,47 +345,78 @@ rhs0_kernel(const RhsParams P) {
 //   sums: |x_i - z'|^2, |x_j - z'|^2, |z' - z|^2 (:240-249), and the block_5 penalty
 //         sum q_ij (x_i - (z - y_i))^2 evaluated with the OLD z, y (objective value, block_5:24-27).
 // =================================================================================================
+struct EdgePtrs {
+    const float *xi, *xj, *ai_r, *aj_r, *Wi, *Wj, *qij, *qji;
+    float *yi, *yj, *z;
+    float q_uniform;
+};
+
+__device__ __forceinline__ void edge_elem(const EdgePtrs& e, float zo, float xiv, float yiv, float xjv, float yjv,
+                                          float air, float ajr, float wi, float wj, float qi, float qj, float& zn,
+                                          float& yin, float& yjn, float (&s)[5]) {
+    float ai, aj;
+    if (e.xi) {
+        ai = xiv + yiv;
+        const float ei = xiv - (zo - yiv);
+        s[3] = fmaf(qi * ei, ei, s[3]);
+    } else ai = air;
+    if (e.xj) {
+        aj = xjv + yjv;
+        const float ej = xjv - (zo - yjv);
+        s[4] = fmaf(qj * ej, ej, s[4]);
+    } else aj = ajr;
+    if (e.Wi) zn = (wi * ai + wj * aj) / (wi + wj);
+    else zn = (ai + aj) / 2.0f;
+    if (e.xi) { const float ri = xiv - zn; yin = yiv + xiv - zn; s[0] = fmaf(ri, ri, s[0]); }
+    if (e.xj) { const float rj = xjv - zn; yjn = yjv + xjv - zn; s[1] = fmaf(rj, rj, s[1]); }
+    const float dz = zn - zo;
+    s[2] = fmaf(dz, dz, s[2]);
+}
+
 __global__ void __launch_bounds__(256)
 edge_kernel(const EdgeParams P) {
     __shared__ float red[160];
-    const EdgeDesc e = P.edges[blockIdx.y];
-    const float* __restrict__ xi = reinterpret_cast<const float*>(e.xi);
-    const float* __restrict__ xj = reinterpret_cast<const float*>(e.xj);
-    float* __restrict__ yi = reinterpret_cast<float*>(e.yi);
-    float* __restrict__ yj = reinterpret_cast<float*>(e.yj);
-    float* __restrict__ z = reinterpret_cast<float*>(e.z);
-    const float* __restrict__ ai_r = reinterpret_cast<const float*>(e.ai);
-    const float* __restrict__ aj_r = reinterpret_cast<const float*>(e.aj);
-    const float* __restrict__ Wi = reinterpret_cast<const float*>(e.Wi);
-    const float* __restrict__ Wj = reinterpret_cast<const float*>(e.Wj);
-    const float* __restrict__ qij = reinterpret_cast<const float*>(e.qij);
-    const float* __restrict__ qji = reinterpret_cast<const float*>(e.qji);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += (long long)gridDim.x * blockDim.x) {
-        const float zo = z[k];
-        float xiv = 0.f, yiv = 0.f, xjv = 0.f, yjv = 0.f, ai, aj;
-        if (xi) {
-            xiv = xi[k]; yiv = yi[k]; ai = xiv + yiv;
-            const float ei = xiv - (zo - yiv);
-            s3 = fmaf((qij ? qij[k] : P.q_uniform) * ei, ei, s3);
-        } else ai = ai_r[k];
-        if (xj) {
-            xjv = xj[k]; yjv = yj[k]; aj = xjv + yjv;
-            const float ej = xjv - (zo - yjv);
-            s4 = fmaf((qji ? qji[k] : P.q_uniform) * ej, ej, s4);
-        } else aj = aj_r[k];
-        float zn;
-        if (Wi) { const float wi = Wi[k], wj = Wj[k]; zn = (wi * ai + wj * aj) / (wi + wj); }
-        else zn = (ai + aj) / 2.0f;
-        if (xi) { const float ri = xiv - zn; yi[k] = yiv + xiv - zn; s0 = fmaf(ri, ri, s0); }
-        if (xj) { const float rj = xjv - zn; yj[k] = yjv + xjv - zn; s1 = fmaf(rj, rj, s1); }
-        const float dz = zn - zo;
-        s2 = fmaf(dz, dz, s2);
-        z[k] = zn;
+    const EdgeDesc d = P.edges[blockIdx.y];
+    EdgePtrs e;
+    e.xi = reinterpret_cast<const float*>(d.xi); e.xj = reinterpret_cast<const float*>(d.xj);
+    e.yi = reinterpret_cast<float*>(d.yi); e.yj = reinterpret_cast<float*>(d.yj);
+    e.z = reinterpret_cast<float*>(d.z);
+    e.ai_r = reinterpret_cast<const float*>(d.ai); e.aj_r = reinterpret_cast<const float*>(d.aj);
+    e.Wi = reinterpret_cast<const float*>(d.Wi); e.Wj = reinterpret_cast<const float*>(d.Wj);
+    e.qij = reinterpret_cast<const float*>(d.qij); e.qji = reinterpret_cast<const float*>(d.qji);
+    e.q_uniform = P.q_uniform;
+    float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 qu4 = make_float4(P.q_uniform, P.q_uniform, P.q_uniform, P.q_uniform);
+    const long long n4 = ((P.n & 3) == 0) ? (P.n >> 2) : 0;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x) {
+        const long long o = 4 * k;
+        const float4 zo = ld4(e.z + o);
+        const float4 xi = e.xi ? ld4(e.xi + o) : zero4, yi = e.xi ? ld4(e.yi + o) : zero4;
+        const float4 xj = e.xj ? ld4(e.xj + o) : zero4, yj = e.xj ? ld4(e.yj + o) : zero4;
+        const float4 ar = e.xi ? zero4 : ld4(e.ai_r + o), br = e.xj ? zero4 : ld4(e.aj_r + o);
+        const float4 wi = e.Wi ? ld4(e.Wi + o) : zero4, wj = e.Wi ? ld4(e.Wj + o) : zero4;
+        const float4 qi = (e.xi && e.qij) ? ld4(e.qij + o) : qu4, qj = (e.xj && e.qji) ? ld4(e.qji + o) : qu4;
+        float4 zn, yin = zero4, yjn = zero4;
+        edge_elem(e, zo.x, xi.x, yi.x, xj.x, yj.x, ar.x, br.x, wi.x, wj.x, qi.x, qj.x, zn.x, yin.x, yjn.x, s);
+        edge_elem(e, zo.y, xi.y, yi.y, xj.y, yj.y, ar.y, br.y, wi.y, wj.y, qi.y, qj.y, zn.y, yin.y, yjn.y, s);
+        edge_elem(e, zo.z, xi.z, yi.z, xj.z, yj.z, ar.z, br.z, wi.z, wj.z, qi.z, qj.z, zn.z, yin.z, yjn.z, s);
+        edge_elem(e, zo.w, xi.w, yi.w, xj.w, yj.w, ar.w, br.w, wi.w, wj.w, qi.w, qj.w, zn.w, yin.w, yjn.w, s);
+        st4(e.z + o, zn);
+        if (e.xi) st4(e.yi + o, yin);
+        if (e.xj) st4(e.yj + o, yjn);
     }
-    float v[5] = {s0, s1, s2, s3, s4};
-    block_sum<5>(v, red);
-    grid_reduce_store<5>(v, P.part + (long long)blockIdx.y * gridDim.x * 5, P.counter + blockIdx.y, blockIdx.x,
+    for (long long k = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += (long long)gridDim.x * blockDim.x) {
+        float zn, yin = 0.f, yjn = 0.f;
+        edge_elem(e, e.z[k], e.xi ? e.xi[k] : 0.f, e.xi ? e.yi[k] : 0.f, e.xj ? e.xj[k] : 0.f, e.xj ? e.yj[k] : 0.f,
+                  e.xi ? 0.f : e.ai_r[k], e.xj ? 0.f : e.aj_r[k], e.Wi ? e.Wi[k] : 0.f, e.Wi ? e.Wj[k] : 0.f,
+                  (e.xi && e.qij) ? e.qij[k] : P.q_uniform, (e.xj && e.qji) ? e.qji[k] : P.q_uniform, zn, yin, yjn, s);
+        e.z[k] = zn;
+        if (e.xi) e.yi[k] = yin;
+        if (e.xj) e.yj[k] = yjn;
+    }
+    block_sum<5>(s, red);
+    grid_reduce_store<5>(s, P.part + (long long)blockIdx.y * gridDim.x * 5, P.counter + blockIdx.y, blockIdx.x,
                          gridDim.x, P.sums + (long long)blockIdx.y * 5, red);
 }
 
@@ -286,7 +427,12 @@ pack_kernel(const PackParams P) {
     const float* __restrict__ x = reinterpret_cast<const float*>(d.x);
     const float* __restrict__ y = reinterpret_cast<const float*>(d.y);
     float* __restrict__ o = reinterpret_cast<float*>(d.out);
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += (long long)gridDim.x * blockDim.x)
+    const long long n4 = ((P.n & 3) == 0) ? (P.n >> 2) : 0;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x) {
+        const float4 a = ld4(x + 4 * k), b = ld4(y + 4 * k);
+        st4(o + 4 * k, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w));
+    }
+    for (long long k = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += (long long)gridDim.x * blockDim.x)
         o[k] = x[k] + y[k];
 }
 
@@ -333,8 +479,8 @@ static inline int stream_blocks(long long n, int per_thread) {
 }
 
 cudaError_t launch_tv(const TvParams& P, int nodes, cudaStream_t st) {
-    dim3 grid((P.N + TT - 1) / TT, (P.N + TT - 1) / TT, nodes);
-    { ProfScope ps(KC_TV, st); tv_fused_kernel<<<grid, 256, 0, st>>>(P); }
+    dim3 grid((P.N + 4 * TVX - 1) / (4 * TVX), (P.N + TVY - 1) / TVY, nodes);
+    { ProfScope ps(KC_TV, st); tv_fused_kernel<<<grid, dim3(TVX, TVY), 0, st>>>(P); }
     return cudaGetLastError();
 }
 cudaError_t launch_cg_update(const CgParams& P, int nodes, int nblk, cudaStream_t st) {
