@@ -48,6 +48,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                        # --- B200 solver controls (not in the reference) ---
                        cg_iters=8, tv_sweeps=1, tv_mu=None, node_prec=None, weighted_z=False, scs_eps=None,
                        check_every=1, node_group=None, fuse_pupdate=True, device=None, return_engine=False,
+                       distributed=None,
                        **kwargs):
     """Returns x_per_node as list of reconstructions, each length n, and the history of residual norms
     (block_6_admm_loop_ver2.py:21-24).
@@ -55,7 +56,8 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
     `max_inner_iters` caps the CG iterations per TV sweep (it is unused in the reference, :17); `cg_iters`,
     `tv_sweeps`, `tv_mu` select the inner work, which is fixed per outer iteration (no host round trips).
     `Qij_diag_fn` may be a callable (i, j) -> n-vector (block_3 provider), a scalar, or None (uniform 1).
-    Under torch.distributed (NCCL) the nodes are sharded over the ranks; every rank returns the full result.
+    Under torch.distributed (NCCL) the nodes are sharded over the ranks; every rank returns the full result
+    (`distributed=False` keeps the whole graph on this rank's GPU).
     """
     for k in list(kwargs):
         if k in _IGNORED:
@@ -81,7 +83,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
     import torch
     import torch.distributed as dist
     world, rank, group = 1, 0, None
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if distributed is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         world, rank = dist.get_world_size(), dist.get_rank()
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else torch.cuda.current_device()
@@ -96,9 +98,11 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
     print(f"Max ADMM Iteration in Block-6 B4 Loop = {max_iters}") if verbose else None
 
     def snapshot(k, e):  # :269-281 (npy only; PNGs need matplotlib, which the hot path does not import)
-        if snapshot_dir is not None and ((k + 1) % snapshot_every == 0) and rank == 0:
-            for i, xi in enumerate(e.x_all()):
-                np.save(os.path.join(snapshot_dir, f"iter_{k+1:04d}_node_{i}.npy"), xi.reshape(N, N))
+        if snapshot_dir is not None and ((k + 1) % snapshot_every == 0):
+            xs = e.x_all()                      # collective when sharded: every rank takes part
+            if rank == 0:
+                for i, xi in enumerate(xs):
+                    np.save(os.path.join(snapshot_dir, f"iter_{k+1:04d}_node_{i}.npy"), xi.reshape(N, N))
 
     t0 = time.perf_counter()
     iters = solve(eng, max_iters, eps_pri, eps_dual, verbose=verbose, stop=True, check_every=check_every,

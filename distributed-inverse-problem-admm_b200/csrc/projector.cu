@@ -80,7 +80,7 @@ fwd_strip_kernel(const FwdParams P) {
     const int slot = tid / FTPA, t = tid % FTPA;
     const int nslab = (Kseg + FL - 1) / FL;
     // shared-window byte address of S[0][-1+1] minus the magic-number bias: addr(k, i) = sbase + k*pitch*4 + bits(i)*4
-    const unsigned sbase = smem_u32(S) + 4u - ((unsigned)kMagicBits << 2);
+    const unsigned sbase = smem_u32(S) + 4u * FHALO - ((unsigned)kMagicBits << 2);
     for (int slab = 0; slab < nslab; ++slab) {
         const int K0 = K0seg + slab * FL, Lt = min(FL, K0seg + Kseg - K0);
         __syncthreads();  // previous slab fully consumed (also orders the acc/zero + setup writes)
@@ -121,7 +121,7 @@ fwd_strip_kernel(const FwdParams P) {
                         val = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
                     }
                 }
-                float* dst = S + k4 * FPITCH + 1 + u;
+                float* dst = S + k4 * FPITCH + FHALO + u;
                 dst[0] = val.x; dst[FPITCH] = val.y; dst[2 * FPITCH] = val.z; dst[3 * FPITCH] = val.w;
             }
         } else {
@@ -134,13 +134,15 @@ fwd_strip_kernel(const FwdParams P) {
                     x = img[g];
                     if (rimg) { x = fmaf(beta, x, rimg[g]); if (pout) pout[g] = x; }
                 }
-                S[k * FPITCH + 1 + u] = x;
+                S[k * FPITCH + FHALO + u] = x;
             }
         }
         for (int k = tid; k < FL; k += FTHREADS) {
             S[k * FPITCH] = 0.f;
-            S[k * FPITCH + FW + 1] = 0.f;
+            S[k * FPITCH + 1] = 0.f;
             S[k * FPITCH + FW + 2] = 0.f;
+            S[k * FPITCH + FW + 3] = 0.f;
+            S[k * FPITCH + FW + 4] = 0.f;
         }
         __syncthreads();
         // ---- sample ---------------------------------------------------------------------------------
@@ -153,21 +155,16 @@ fwd_strip_kernel(const FwdParams P) {
             const int jseg = s_jseg[ai];
             for (int j = win.x + t; j <= win.y; j += FTPA) {
                 const float u0 = ((float)(j - win.z) - fb) * im;   // u_k = u0 - k s  (interp-axis pixel coordinate)
+                // steps with -1 <= u_k <= Wt.  The float bounds may be off by one step at either end, which moves u
+                // by < 1 pixel: the two-column zero halo makes such a sample contribute exactly 0, and a dropped
+                // boundary sample has weight ~0, so no exact fix-up loop is needed.
                 int klo = 0, khi = Lt - 1;
                 if (rs != 0.f) {
                     const float ka = (u0 - uhi) * rs, kb = (u0 - ulo) * rs;
-                    klo = max(0, (int)fmaxf(ceilf(fminf(ka, kb)) - 1.f, -1.f));
-                    khi = min(Lt - 1, (int)fminf(floorf(fmaxf(ka, kb)) + 1.f, (float)FL));
-                }
-                while (klo <= khi) {
-                    const float u = fmaf(-(float)klo, s, u0);
-                    if (u >= ulo && u <= uhi) break;
-                    ++klo;
-                }
-                while (klo <= khi) {
-                    const float u = fmaf(-(float)khi, s, u0);
-                    if (u >= ulo && u <= uhi) break;
-                    --khi;
+                    klo = max(0, (int)ceilf(fminf(ka, kb)));
+                    khi = min(Lt - 1, (int)floorf(fmaxf(ka, kb)));
+                } else if (u0 < ulo || u0 > uhi) {
+                    khi = -1;
                 }
                 float acc = 0.f;
                 float kf = (float)klo;
@@ -240,43 +237,52 @@ back_tile_kernel(const BackParams P) {
     float* qs = reinterpret_cast<float*>(smem_raw);       // [BAC][bspan]
     float4* s_c = reinterpret_cast<float4*>(qs + BAC * P.bspan + ((4 - ((BAC * P.bspan) & 3)) & 3));  // [BAC]
     unsigned* s_qa = reinterpret_cast<unsigned*>(s_c + BAC);  // [BAC] biased shared-window address of each window
+    int* s_jw = reinterpret_cast<int*>(s_qa + BAC);           // [BAC] first detector bin of each window
+    float* s_sc = reinterpret_cast<float*>(s_jw + BAC);       // [BAC] window scale (step weight * precision)
     __shared__ float red[64];
 
     const int node = P.node0 + blockIdx.z;
     const int N = P.N, D = P.D, bspan = P.bspan;
     const int X0 = blockIdx.y * BTX, Y0 = blockIdx.x * BTY;
     const int tid = threadIdx.x;
-    const int lx = tid / (BTY / 4), ly = (tid % (BTY / 4)) * 4;
-    const int ix = X0 + lx, iy = Y0 + ly;
+    const int lx = tid >> 3, ly = (tid & 7) * 4;          // pixels (X0+lx, Y0+ly+{0..3}) and (.., Y0+32+ly+{0..3})
+    const int ix = X0 + lx;
     const int abeg = P.aptr[node], aend = P.aptr[node + 1];
     const double cx = 0.5 * (N - 1), cj = 0.5 * (D - 1);
     const float prec = (MODE == BACK_COLNORM2 || P.prec == nullptr) ? 1.f : P.prec[node];
 
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float fx = (float)lx, fy = (float)ly;
     opaque(fx);
     opaque(fy);
     for (int c0 = abeg; c0 < aend; c0 += BAC) {
         const int na = min(BAC, aend - c0);
         __syncthreads();
-        // stage detector windows: one warp per angle row
-        for (int ai = tid / 32; ai < na; ai += BTHREADS / 32) {
-            const AngleRec r = P.ang[c0 + ai];
+        // window geometry: one thread per angle (fp64 once per (tile, angle))
+        if (tid < na) {
+            const AngleRec r = P.ang[c0 + tid];
             const double tau0 = cj + (X0 - cx) * r.ct + (Y0 - cx) * r.st;  // tau of tile pixel (0,0)
             const double e1 = (BTX - 1) * r.ct, e2 = (BTY - 1) * r.st;
             const double om = (double)(1.0f / r.inv_om);
             const int jw0 = (int)floor(tau0 + fmin(e1, 0.0) + fmin(e2, 0.0) - om) - 1;
-            const float sc = (MODE == BACK_COLNORM2) ? r.wgt * r.wgt : r.wgt * prec;
+            // window-relative tau of pixel (0,0), pre-biased by -1/2 for the rint trick
+            s_c[tid] = make_float4((float)(tau0 - (double)jw0 - 0.5), (float)r.ct, (float)r.st, r.inv_om);
+            // read back through shared memory so the magic-number bias stays folded into ONE register
+            s_qa[tid] = smem_u32(qs) + (unsigned)(tid * bspan * 4) - ((unsigned)kMagicBits << 2);
+            s_jw[tid] = jw0;
+            s_sc[tid] = (MODE == BACK_COLNORM2) ? r.wgt * r.wgt : r.wgt * prec;
+        }
+        __syncthreads();
+        // stage the detector windows: one warp per angle row, coalesced
+        for (int ai = tid >> 5; ai < na; ai += BTHREADS / 32) {
+            const int jw0 = s_jw[ai];
+            const float sc = s_sc[ai];
+            const float* __restrict__ qrow = P.q + (long long)(c0 + ai) * D;
             for (int k = (tid & 31); k < bspan; k += 32) {
                 const int j = jw0 + k;
                 float val = 0.f;
-                if (j >= 0 && j < D) val = (MODE == BACK_COLNORM2) ? sc : sc * P.q[(long long)(c0 + ai) * D + j];
+                if (j >= 0 && j < D) val = (MODE == BACK_COLNORM2) ? sc : sc * qrow[j];
                 qs[ai * bspan + k] = val;
-            }
-            if ((tid & 31) == 0) {  // window-relative tau of pixel (0,0), pre-biased by -1/2 for the rint trick
-                s_c[ai] = make_float4((float)(tau0 - (double)jw0 - 0.5), (float)r.ct, (float)r.st, r.inv_om);
-                // read back through shared memory so the magic-number bias stays folded into ONE register
-                s_qa[ai] = smem_u32(qs) + (unsigned)(ai * bspan * 4) - ((unsigned)kMagicBits << 2);
             }
         }
         __syncthreads();
@@ -288,8 +294,9 @@ back_tile_kernel(const BackParams P) {
                 const float c1 = fmaf(-0.5f, a, 1.f);
                 const unsigned qa = s_qa[ai];
 #pragma unroll
-                for (int px = 0; px < 4; ++px) {
-                    const float v = (px == 0) ? tb : fmaf((float)px, c.z, tb);
+                for (int px = 0; px < 8; ++px) {
+                    const float off = (float)((px & 3) + 32 * (px >> 2));
+                    const float v = (px == 0) ? tb : fmaf(off, c.z, tb);
                     const float fi = v + kMagic;
                     const float up = v - (fi - kMagic);               // in [-1/2, 1/2]
                     const unsigned addr = (__float_as_uint(fi) << 2) + qa;
@@ -303,8 +310,9 @@ back_tile_kernel(const BackParams P) {
                 const float* __restrict__ qa = qs + ai * bspan;
                 const float om = 1.f / a;
 #pragma unroll
-                for (int px = 0; px < 4; ++px) {
-                    const float tau = fmaf((float)px, c.z, tb) + 0.5f;
+                for (int px = 0; px < 8; ++px) {
+                    const float off = (float)((px & 3) + 32 * (px >> 2));
+                    const float tau = fmaf(off, c.z, tb) + 0.5f;
                     const int jlo = (int)ceilf(tau - om), jhi = (int)floorf(tau + om);
                     for (int j = max(jlo, 0); j <= min(jhi, bspan - 1); ++j) {
                         float w = fmaxf(0.f, 1.f - fabsf(tau - (float)j) * a);
@@ -319,63 +327,97 @@ back_tile_kernel(const BackParams P) {
     // ---- epilogue ----------------------------------------------------------------------------------
     const long long nb = (long long)blockIdx.z * P.stride;
     const bool rowok = ix < N;
+    const bool vecok = (N & 3) == 0;
     float dsum = 0.f;
     if (MODE == BACK_PLAIN || MODE == BACK_COLNORM2) {
         if (rowok) {
-            float* o = P.out + nb + (long long)ix * N + iy;
-            if (iy + 3 < N && (N & 3) == 0) st4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
-            else for (int px = 0; px < 4; ++px) if (iy + px < N) o[px] = acc[px];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int iy = Y0 + ly + 32 * h;
+                float* o = P.out + nb + (long long)ix * N + iy;
+                if (iy + 3 < N && vecok) st4(o, make_float4(acc[4 * h], acc[4 * h + 1], acc[4 * h + 2], acc[4 * h + 3]));
+                else for (int px = 0; px < 4; ++px) if (iy + px < N) o[px] = acc[4 * h + px];
+            }
         }
         return;
     } else {
-        if (rowok) {
-            const float* __restrict__ v = P.v + nb;
+        const float* __restrict__ v = P.v + nb;
+        const float rhoDs = P.rhoD_vec ? 0.f : P.rhoD_s[node];
+        // tiles that touch no image border take the unguarded path
+        const bool interior = vecok && X0 >= 1 && X0 + BTX < N && Y0 >= 1 && Y0 + BTY < N;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int iy = Y0 + ly + 32 * h;
             const long long g = (long long)ix * N + iy;
-            float vc[6], vu[4], vd[4];  // centre row with one halo each side, up row, down row
-#pragma unroll
-            for (int px = -1; px < 5; ++px) {
-                const int y = iy + px;
-                vc[px + 1] = (y >= 0 && y < N) ? v[g + px] : 0.f;
-            }
-#pragma unroll
-            for (int px = 0; px < 4; ++px) {
-                const bool ok = iy + px < N;
-                vu[px] = (ok && ix >= 1) ? v[g + px - N] : 0.f;
-                vd[px] = (ok && ix + 1 < N) ? v[g + px + N] : 0.f;
-            }
-            const float rhoDs = P.rhoD_vec ? 0.f : P.rhoD_s[node];
             float res[4];
-#pragma unroll
-            for (int px = 0; px < 4; ++px) {
-                const int y = iy + px;
-                if (y >= N) { res[px] = 0.f; continue; }
-                const float c = vc[px + 1];
-                float lap = 0.f;
-                if (ix >= 1) lap += c - vu[px];
-                if (ix + 1 < N) lap += c - vd[px];
-                if (y >= 1) lap += c - vc[px];
-                if (y + 1 < N) lap += c - vc[px + 2];
-                const float dd = P.rhoD_vec ? P.rhoD_vec[nb + g + px] : rhoDs;
-                const float hv = acc[px] + fmaf(dd, c, P.mu * lap);
-                if (MODE == BACK_HP) {
-                    res[px] = hv;
-                    dsum = fmaf(c, hv, dsum);
-                } else {
-                    const float rr = (P.rhs0[nb + g + px] + P.tvterm[nb + g + px]) - hv;
-                    res[px] = rr;
-                    dsum = fmaf(rr, rr, dsum);
+            if (interior) {
+                const float4 c4 = ld4(v + g), u4 = ld4(v + g - N), d4 = ld4(v + g + N);
+                const float lf = v[g - 1], rt = v[g + 4];
+                const float vc[6] = {lf, c4.x, c4.y, c4.z, c4.w, rt};
+                const float vu[4] = {u4.x, u4.y, u4.z, u4.w}, vd[4] = {d4.x, d4.y, d4.z, d4.w};
+                float dd[4] = {rhoDs, rhoDs, rhoDs, rhoDs};
+                if (P.rhoD_vec) { const float4 t = ld4(P.rhoD_vec + nb + g); dd[0] = t.x; dd[1] = t.y; dd[2] = t.z; dd[3] = t.w; }
+                float rh[4] = {0.f, 0.f, 0.f, 0.f};
+                if (MODE == BACK_RESID0) {
+                    const float4 r0 = ld4(P.rhs0 + nb + g), t0 = ld4(P.tvterm + nb + g);
+                    rh[0] = r0.x + t0.x; rh[1] = r0.y + t0.y; rh[2] = r0.z + t0.z; rh[3] = r0.w + t0.w;
                 }
-            }
-            float* o = P.out + nb + g;
-            if (iy + 3 < N && (N & 3) == 0) {
-                st4(o, make_float4(res[0], res[1], res[2], res[3]));
+#pragma unroll
+                for (int px = 0; px < 4; ++px) {
+                    const float c = vc[px + 1];
+                    const float lap = ((c - vu[px]) + (c - vd[px])) + ((c - vc[px]) + (c - vc[px + 2]));
+                    const float hv = acc[4 * h + px] + fmaf(dd[px], c, P.mu * lap);
+                    if (MODE == BACK_HP) { res[px] = hv; dsum = fmaf(c, hv, dsum); }
+                    else { const float rr = rh[px] - hv; res[px] = rr; dsum = fmaf(rr, rr, dsum); }
+                }
+                st4(P.out + nb + g, make_float4(res[0], res[1], res[2], res[3]));
                 if (MODE == BACK_RESID0) st4(P.p_out + nb + g, make_float4(res[0], res[1], res[2], res[3]));
-            } else {
-                for (int px = 0; px < 4; ++px)
-                    if (iy + px < N) {
-                        o[px] = res[px];
-                        if (MODE == BACK_RESID0) P.p_out[nb + g + px] = res[px];
+            } else if (rowok && iy < N) {
+                float vc[6], vu[4], vd[4];  // centre row with one halo each side, up row, down row
+#pragma unroll
+                for (int px = -1; px < 5; ++px) {
+                    const int y = iy + px;
+                    vc[px + 1] = (y >= 0 && y < N) ? v[g + px] : 0.f;
+                }
+#pragma unroll
+                for (int px = 0; px < 4; ++px) {
+                    const bool ok = iy + px < N;
+                    vu[px] = (ok && ix >= 1) ? v[g + px - N] : 0.f;
+                    vd[px] = (ok && ix + 1 < N) ? v[g + px + N] : 0.f;
+                }
+#pragma unroll
+                for (int px = 0; px < 4; ++px) {
+                    const int y = iy + px;
+                    if (y >= N) { res[px] = 0.f; continue; }
+                    const float c = vc[px + 1];
+                    float lu = 0.f, ld = 0.f, ll = 0.f, lr = 0.f;   // same association as the interior path
+                    if (ix >= 1) lu = c - vu[px];
+                    if (ix + 1 < N) ld = c - vd[px];
+                    if (y >= 1) ll = c - vc[px];
+                    if (y + 1 < N) lr = c - vc[px + 2];
+                    const float lap = (lu + ld) + (ll + lr);
+                    const float dd = P.rhoD_vec ? P.rhoD_vec[nb + g + px] : rhoDs;
+                    const float hv = acc[4 * h + px] + fmaf(dd, c, P.mu * lap);
+                    if (MODE == BACK_HP) {
+                        res[px] = hv;
+                        dsum = fmaf(c, hv, dsum);
+                    } else {
+                        const float rr = (P.rhs0[nb + g + px] + P.tvterm[nb + g + px]) - hv;
+                        res[px] = rr;
+                        dsum = fmaf(rr, rr, dsum);
                     }
+                }
+                float* o = P.out + nb + g;
+                if (iy + 3 < N && vecok) {
+                    st4(o, make_float4(res[0], res[1], res[2], res[3]));
+                    if (MODE == BACK_RESID0) st4(P.p_out + nb + g, make_float4(res[0], res[1], res[2], res[3]));
+                } else {
+                    for (int px = 0; px < 4; ++px)
+                        if (iy + px < N) {
+                            o[px] = res[px];
+                            if (MODE == BACK_RESID0) P.p_out[nb + g + px] = res[px];
+                        }
+                }
             }
         }
         float vsum[1] = {dsum};
@@ -413,7 +455,7 @@ cudaError_t launch_forward(const FwdParams& P, int nodes, int max_chunks, const 
 cudaError_t launch_back(int mode, const BackParams& P, int nodes, cudaStream_t st) {
     size_t f = (size_t)BAC * P.bspan;
     f += (4 - (f & 3)) & 3;
-    const size_t smem = f * sizeof(float) + BAC * sizeof(float4) + BAC * sizeof(unsigned);
+    const size_t smem = f * sizeof(float) + BAC * sizeof(float4) + BAC * (sizeof(unsigned) + sizeof(int) + sizeof(float));
     dim3 grid((P.N + BTY - 1) / BTY, (P.N + BTX - 1) / BTX, nodes);
     switch (mode) {
         case BACK_PLAIN: { ProfScope ps(KC_BACK_PLAIN, st); back_tile_kernel<BACK_PLAIN><<<grid, BTHREADS, smem, st>>>(P); } break;

@@ -5,13 +5,14 @@
 namespace admm {
 
 // ---- K1 forward: strip/segment decomposition ----------------------------------------------------
-constexpr int FW = 120;       // interpolation-axis extent of a strip (pixels)
-constexpr int FL = 32;        // steps per staged slab
+constexpr int FW = 108;       // interpolation-axis extent of a strip: sqrt((FW+2)^2 + (FL-1)^2) + 1 <= FTPA
+constexpr int FL = 64;        // steps per staged slab
 constexpr int FSEG_MAX = 256; // max steps per block segment (the plan picks seg <= FSEG_MAX, a multiple of FL)
 constexpr int FTPA = 128;     // threads per angle slot (bins handled per round)
 constexpr int FAC = 16;       // angles per block chunk
 constexpr int FTHREADS = 256; // 2 angle slots
-constexpr int FPITCH = FW + 3;  // smem row pitch (odd): [-1 halo][0..FW)[2 zero columns]
+constexpr int FPITCH = FW + 5;  // smem row pitch (odd): [2 zero columns][0..FW)[3 zero columns]
+constexpr int FHALO = 2;        // leading zero columns
 
 struct FwdParams {
     const float* img;        // [nodes][N*N] images to project (p or x)
@@ -44,8 +45,8 @@ struct FwdReduceParams {
 
 // ---- K2 back-projection (gather) with fused epilogues ---------------------------------------------
 constexpr int BTX = 32;        // tile rows (ix)
-constexpr int BTY = 32;        // tile cols (iy)
-constexpr int BTHREADS = 256;  // 4 pixels (along iy) per thread
+constexpr int BTY = 64;        // tile cols (iy)
+constexpr int BTHREADS = 256;  // 8 pixels per thread: two float4 groups 32 columns apart
 constexpr int BAC = 16;        // angles staged per chunk
 
 enum BackMode : int {
