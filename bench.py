@@ -405,7 +405,8 @@ def main():
         e2e = {"value": args.steps / dt, "unit": "iters/s", "h2d_bytes_per_step": int(h2d / args.steps),
                "d2h_bytes_per_step": int(d2h / args.steps), "call": "block_6_admm_loop_ver2.decentralized_admm(host numpy "
                "sinograms) -> (host x list, history); includes plan build, uploads, A^T b, per-iteration residual "
-               "read-back for the stop test, final x download", "wall_s": round(dt, 3), "iters": len(hist["primal"])}
+               "read-back for the stop test, final x download", "wall_s": round(dt, 3), "iters": len(hist["primal"]),
+               "timing_s": {k: round(v, 4) for k, v in hist.get("timing_s", {}).items()}}
         e2.close()
 
     cpu = None

@@ -138,6 +138,21 @@ class ADMMEngine:
         self.send = {p: z(len(sp.exch[p]), n) for p in sp.peers}
         self.recv = {p: z(len(sp.exch[p]), n) for p in sp.peers}
 
+        # the (pinned) host landing buffer of the final x download is page-locked in the background while the
+        # GPU iterates (cudaHostAlloc of GBs takes longer than the copy itself)
+        self._host_x = None
+        self._host_thread = None
+        if self.world == 1:
+            import threading
+
+            def _alloc():
+                try:
+                    self._host_x = torch.empty((V, n), dtype=torch.float32, pin_memory=True)
+                except Exception:
+                    self._host_x = None
+            self._host_thread = threading.Thread(target=_alloc, daemon=True)
+            self._host_thread.start()
+
         self._build_tables()
         self.st = nat.State()
         self._fill_state(fuse_pupdate)
@@ -305,7 +320,11 @@ class ADMMEngine:
         xl = self.x
         torch = self.torch
         if self.world == 1:
-            host = torch.empty(xl.shape, dtype=torch.float32, pin_memory=True)
+            if self._host_thread is not None:
+                self._host_thread.join()
+                self._host_thread = None
+            host = self._host_x if self._host_x is not None else torch.empty(xl.shape, dtype=torch.float32, pin_memory=True)
+            self._host_x = None          # the caller owns the views from here on
             host.copy_(xl, non_blocking=True)
             torch.cuda.synchronize(self.dev)
             arr = host.numpy()

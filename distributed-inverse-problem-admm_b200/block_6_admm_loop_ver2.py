@@ -88,6 +88,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else torch.cuda.current_device()
 
+    t_start = time.perf_counter()
     eng = ADMMEngine(thetas, sinograms, G, N, D=D, det_w=det_w, lam_tv=lam_tv, rho=rho, Q=Qij_diag_fn,
                      Wi_list=Wi_list, node_prec=node_prec, tv_mu=tv_mu, tv_sweeps=tv_sweeps,
                      cg_iters=min(int(cg_iters), int(max_inner_iters)), phantom_true=phantom_true,
@@ -107,10 +108,14 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
     t0 = time.perf_counter()
     iters = solve(eng, max_iters, eps_pri, eps_dual, verbose=verbose, stop=True, check_every=check_every,
                   snapshot=snapshot if snapshot_dir is not None else None)
+    t1 = time.perf_counter()
     x = eng.x_all()
+    t2 = time.perf_counter()
     history = eng.history(iters)
     history["primal_res"], history["dual_res"], history["obj"] = history["primal"], history["dual"], history["obj_total"]
     history["wall_time_s"] = time.perf_counter() - t0
+    history["timing_s"] = {"setup": t0 - t_start, "iterations": t1 - t0, "download_x": t2 - t1,
+                           "history": time.perf_counter() - t2}
     history["inner"] = {"cg_iters": eng.C, "tv_sweeps": eng.S, "tv_mu": eng.mu}
 
     try:  # :293-306
