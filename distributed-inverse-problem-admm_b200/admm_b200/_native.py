@@ -51,7 +51,8 @@ class State(ctypes.Structure):
                 ("x", "r", "p0", "p1", "hp", "rhs0", "tvterm", "atb", "w0", "w1", "rhoD_vec", "rhoD_s", "prec",
                  "xtrue", "q", "ax", "b", "scal", "part", "counter")] + [
         ("stride", ctypes.c_longlong), ("rho", ctypes.c_float), ("lam", ctypes.c_float), ("mu", ctypes.c_float),
-        ("q_uniform", ctypes.c_float), ("w_parity", ctypes.c_int), ("fuse_pupdate", ctypes.c_int)]
+        ("q_uniform", ctypes.c_float), ("w_parity", ctypes.c_int), ("fuse_pupdate", ctypes.c_int),
+        ("defer_tv", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 EDGE_FIELDS = ("xi", "xj", "yi", "yj", "z", "ai", "aj", "Wi", "Wj", "qij", "qji")  # struct admm_edge (u64 each)
@@ -83,6 +84,8 @@ def lib():
     L.admm_colnorm2.argtypes = [vp, vp, ll, i, i, vp]
     L.admm_forward_host.argtypes = [vp, i, vp, vp]
     L.admm_adjoint_host.argtypes = [vp, i, vp, vp]
+    L.admm_colnorm2_host.argtypes = [vp, i, vp]
+    L.admm_colnorm2_host.restype = i
     L.admm_rhs0.argtypes = [vp, ctypes.POINTER(State), vp, vp, vp, vp, i, i, vp]
     L.admm_x_update.argtypes = [vp, ctypes.POINTER(State), i, i, i, i, vp]
     L.admm_tv_pass.argtypes = [vp, ctypes.POINTER(State), i, i, i, vp]
@@ -103,7 +106,7 @@ def lib():
 
 EXPORTS = ("admm_version", "admm_last_error", "admm_device_count", "admm_plan_create", "admm_plan_destroy",
            "admm_plan_info", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host",
-           "admm_adjoint_host", "admm_rhs0", "admm_x_update", "admm_edge_update", "admm_pack", "admm_finalize",
+           "admm_adjoint_host", "admm_colnorm2_host", "admm_rhs0", "admm_x_update", "admm_edge_update", "admm_pack", "admm_finalize",
            "admm_tv_pass", "admm_launch_count", "admm_profile_enable", "admm_profile_read", "admm_grad2d_host",
            "admm_div2d_host", "admm_kt_subgrad_host")
 

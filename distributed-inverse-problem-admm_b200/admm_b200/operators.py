@@ -266,10 +266,9 @@ class RayTransformCUDA:
         return _Functional(self, self.range.cell_volume / self.domain.cell_volume)
 
     def colnorm2(self):
-        torch = _torch()
-        out = torch.empty(self.shape[1], dtype=torch.float32, device=f"cuda:{self.device}")
-        self.plan().colnorm2(out)
-        return out.cpu().numpy().astype(np.float64)
+        out = np.empty(self.shape[1], dtype=np.float32)
+        nat.check(nat.lib().admm_colnorm2_host(self.plan().handle, 0, out.ctypes.data), "admm_colnorm2_host")
+        return out.astype(np.float64)
 
 
 def stack_operators(ops):

@@ -78,17 +78,22 @@ def build_shard_plan(G, world: int, rank: int) -> ShardPlan:
     return sp
 
 
-def exchange(dist, sp: ShardPlan, send: dict, recv: dict, group=None):
-    """One neighbour exchange: for every peer p, send[p] ([n_cut_p, n], this rank's a = x + y of the cut edges
-    shared with p, in `sp.exch[p]` order) goes to p and p's matching buffer lands in recv[p].  Grouped P2P
-    (ncclSend/ncclRecv inside one group on NCCL; works unchanged on gloo with CPU tensors)."""
+def post_exchange(dist, sp: ShardPlan, send: dict, recv: dict, group=None):
+    """Post one neighbour exchange and return the requests: for every peer p, send[p] ([n_cut_p, n], this rank's
+    a = x + y of the cut edges shared with p, in `sp.exch[p]` order) goes to p and p's matching buffer lands in
+    recv[p].  Grouped P2P (ncclSend/ncclRecv inside one group on NCCL; works unchanged on gloo with CPU tensors)."""
     if not sp.peers:
-        return
+        return []
     ops = []
     for p in sp.peers:
         ops.append(dist.P2POp(dist.isend, send[p], p, group=group))
         ops.append(dist.P2POp(dist.irecv, recv[p], p, group=group))
-    for req in dist.batch_isend_irecv(ops):
+    return dist.batch_isend_irecv(ops)
+
+
+def exchange(dist, sp: ShardPlan, send: dict, recv: dict, group=None):
+    """Blocking form of post_exchange."""
+    for req in post_exchange(dist, sp, send, recv, group):
         req.wait()
 
 

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _native as nat
 from .operators import Plan
-from .sharding import ShardPlan, build_shard_plan, exchange
+from .sharding import ShardPlan, build_shard_plan, post_exchange
 
 
 def _torch():
@@ -142,16 +142,17 @@ class ADMMEngine:
         # GPU iterates (cudaHostAlloc of GBs takes longer than the copy itself)
         self._host_x = None
         self._host_thread = None
-        if self.world == 1:
-            import threading
+        import threading
+        counts = [sum(1 for r in sp.node_rank if r == k) for k in range(self.world)]
+        self._gather_rows = self.world * max(counts) if self.world > 1 else V
 
-            def _alloc():
-                try:
-                    self._host_x = torch.empty((V, n), dtype=torch.float32, pin_memory=True)
-                except Exception:
-                    self._host_x = None
-            self._host_thread = threading.Thread(target=_alloc, daemon=True)
-            self._host_thread.start()
+        def _alloc():
+            try:
+                self._host_x = torch.empty((self._gather_rows, n), dtype=torch.float32, pin_memory=True)
+            except Exception:
+                self._host_x = None
+        self._host_thread = threading.Thread(target=_alloc, daemon=True)
+        self._host_thread.start()
 
         self._build_tables()
         self.st = nat.State()
@@ -190,7 +191,9 @@ class ADMMEngine:
         self.nbr_z, self.nbr_y, self.nbr_q = i64(za), i64(ya), i64(qa)
         # K5 edge descriptors, pack items, finalize tables
         ed, gi, gj, fl, packs = [], [], [], [], []
-        for le in sp.local_edges:
+        ordered = [le for le in sp.local_edges if le.peer < 0] + [le for le in sp.local_edges if le.peer >= 0]
+        self.n_edges_local = sum(1 for le in sp.local_edges if le.peer < 0)
+        for le in ordered:
             s = le.slot
             xi = self._addr(self.x, sp.g2l[le.gi]) if le.i_local else 0
             xj = self._addr(self.x, sp.g2l[le.gj]) if le.j_local else 0
@@ -230,13 +233,15 @@ class ADMMEngine:
         st.rho, st.lam, st.mu, st.q_uniform = self.rho, self.lam, self.mu, self.q_uniform
         st.w_parity = 0
         st.fuse_pupdate = 1 if fuse else 0
+        st.defer_tv = 1 if self.world > 1 else 0
 
     def _stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
 
     # ---- one outer iteration ------------------------------------------------------------------------------
     def nodes_phase(self):
-        """rhs0 assembly (K6) + x-updates (K1-K4) of every local node, node group by node group."""
+        """rhs0 assembly (K6) + x-updates (K1-K4) of every local node, node group by node group.  When the graph is
+        sharded the last TV pass is deferred (see step) so the exchange can start as soon as x is final."""
         L, h, st = nat.lib(), self.plan.handle, self.st
         sref = ctypes.byref(st)
         nat.check(L.admm_rhs0(h, sref, self.nbr_ptr.data_ptr(), self.nbr_z.data_ptr(), self.nbr_y.data_ptr(),
@@ -244,19 +249,36 @@ class ADMMEngine:
         for n0 in range(0, self.V, self.node_group):
             nn = min(self.node_group, self.V - n0)
             nat.check(L.admm_x_update(h, sref, n0, nn, self.S, self.C, self._stream()), "admm_x_update")
-        st.w_parity ^= (self.S & 1)
+        st.w_parity ^= ((self.S - (1 if st.defer_tv else 0)) & 1)
 
-    def exchange_phase(self):
-        if self.n_pack:
-            nat.check(nat.lib().admm_pack(self.plan.handle, self.pack_desc.data_ptr(), self.n_pack, self._stream()),
-                      "admm_pack")
-            exchange(self.dist, self.sp, self.send, self.recv, self.group)
+    def tv_phase(self):
+        """The deferred last TV pass (K3) of every local node."""
+        st = self.st
+        nat.check(nat.lib().admm_tv_pass(self.plan.handle, ctypes.byref(st), 0, self.V, 1, self._stream()), "admm_tv_pass")
+        st.w_parity ^= 1
 
-    def edges_phase(self):
+    def exchange_start(self):
+        """Pack a = x + y of this rank's cut-edge ends and post the grouped NCCL send/recv (returns the requests)."""
+        if not self.n_pack:
+            return []
+        nat.check(nat.lib().admm_pack(self.plan.handle, self.pack_desc.data_ptr(), self.n_pack, self._stream()),
+                  "admm_pack")
+        return post_exchange(self.dist, self.sp, self.send, self.recv, self.group)
+
+    def edges_phase(self, reqs=()):
+        """K5 on the local edges (overlaps the exchange), then on the cut edges, then the residual row."""
         L, h = nat.lib(), self.plan.handle
         sref = ctypes.byref(self.st)
-        nat.check(L.admm_edge_update(h, sref, self.edge_desc.data_ptr(), self.E, self.sums.data_ptr(), self._stream()),
-                  "admm_edge_update")
+        nl, E = self.n_edges_local, self.E
+        esz = 11 * 8
+        if nl:
+            nat.check(L.admm_edge_update(h, sref, self.edge_desc.data_ptr(), nl, self.sums.data_ptr(), self._stream()),
+                      "admm_edge_update")
+        for r in reqs:
+            r.wait()          # stream-level wait: the compute stream now depends on the received buffers
+        if E - nl:
+            nat.check(L.admm_edge_update(h, sref, self.edge_desc.data_ptr() + nl * esz, E - nl,
+                                         self.sums.data_ptr() + nl * 5 * 8, self._stream()), "admm_edge_update")
         nat.check(L.admm_finalize(h, sref, self.sums.data_ptr(), self.edge_gi.data_ptr(), self.edge_gj.data_ptr(),
                                   self.edge_fl.data_ptr(), self.E, self.node_gid.data_ptr(), self.Vg,
                                   self.row.data_ptr(), self._stream()), "admm_finalize")
@@ -267,8 +289,11 @@ class ADMMEngine:
 
     def step(self):
         self.nodes_phase()
-        self.exchange_phase()
-        self.edges_phase()
+        reqs = ()
+        if self.world > 1:
+            reqs = self.exchange_start()      # x is final: the exchange runs under the TV pass and the local edges
+            self.tv_phase()
+        self.edges_phase(reqs)
         self.k += 1
 
     # ---- results --------------------------------------------------------------------------------------------
@@ -316,29 +341,33 @@ class ADMMEngine:
 
     def x_all(self):
         """x of every node on every rank: list of V float32 arrays of length n (views of one pinned host buffer;
-        the reference's are float64 -- `np.stack`, `.reshape(N, N)` and arithmetic behave the same)."""
-        xl = self.x
+        the reference's are float64 -- `np.stack`, `.reshape(N, N)` and arithmetic behave the same).  When the graph
+        is sharded this is a collective (all_gather over NVLink) and every rank returns the full list."""
         torch = self.torch
+        if self._host_thread is not None:
+            self._host_thread.join()
+            self._host_thread = None
+        host = self._host_x
+        if host is None:
+            host = torch.empty((self._gather_rows, self.n), dtype=torch.float32, pin_memory=True)
+        self._host_x = None          # the caller owns the views from here on
         if self.world == 1:
-            if self._host_thread is not None:
-                self._host_thread.join()
-                self._host_thread = None
-            host = self._host_x if self._host_x is not None else torch.empty(xl.shape, dtype=torch.float32, pin_memory=True)
-            self._host_x = None          # the caller owns the views from here on
-            host.copy_(xl, non_blocking=True)
+            host.copy_(self.x, non_blocking=True)
             torch.cuda.synchronize(self.dev)
             arr = host.numpy()
             return [arr[i] for i in range(self.V)]
         counts = [sum(1 for r in self.sp.node_rank if r == k) for k in range(self.world)]
         mx = max(counts)
         pad = torch.zeros(mx, self.n, dtype=torch.float32, device=self.dev)
-        pad[: self.V] = xl
-        bufs = [torch.empty_like(pad) for _ in range(self.world)]
-        self.dist.all_gather(bufs, pad, group=self.group)
+        pad[: self.V] = self.x
+        gathered = torch.empty(self.world * mx, self.n, dtype=torch.float32, device=self.dev)
+        self.dist.all_gather_into_tensor(gathered, pad, group=self.group)
+        host.copy_(gathered, non_blocking=True)
+        torch.cuda.synchronize(self.dev)
+        arr = host.numpy()
         out = []
         for k in range(self.world):
-            a = bufs[k][: counts[k]].cpu().numpy()
-            out.extend(a[i] for i in range(counts[k]))
+            out.extend(arr[k * mx + i] for i in range(counts[k]))
         return out
 
     def close(self):

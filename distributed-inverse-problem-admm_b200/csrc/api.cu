@@ -321,6 +321,17 @@ extern "C" int admm_adjoint_host(admm_plan* p, int node, const float* h_sino, fl
     return ADMM_OK;
 }
 
+extern "C" int admm_colnorm2_host(admm_plan* p, int node, float* h_img) {
+    if (int e = check_nodes(p, node, 1)) return e;
+    if (!h_img) return fail(ADMM_ERR_ARG, "admm_colnorm2_host: null buffer");
+    CK(cudaSetDevice(p->device));
+    if (int e = host_scratch(p, p->A)) return e;
+    const size_t n = (size_t)p->N * p->N;
+    if (int e = admm_colnorm2(p, p->d_himg, (long long)n, node, 1, nullptr)) return e;
+    CK(cudaMemcpy(h_img, p->d_himg, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return ADMM_OK;
+}
+
 extern "C" int admm_rhs0(admm_plan* p, const admm_state* s, const int* d_nbr_ptr, const unsigned long long* d_nbr_z,
                          const unsigned long long* d_nbr_y, const unsigned long long* d_nbr_q, int node0, int nodes,
                          void* stream) {
@@ -422,8 +433,10 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
             nb = std::max(1LL, std::min(nb, 4096LL));
             CK(launch_cg_update(U, nodes, (int)nb, st));
         }
-        CK(launch_tv(make_tv(p, s, node0, true, parity), nodes, st));
-        parity ^= 1;
+        if (!(s->defer_tv && sw == sweeps - 1)) {
+            CK(launch_tv(make_tv(p, s, node0, true, parity), nodes, st));
+            parity ^= 1;
+        }
     }
     CK(launch_sino_resid(SP, nodes, st));
     return ADMM_OK;

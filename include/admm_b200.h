@@ -66,6 +66,9 @@ typedef struct admm_state {
     float rho, lam, mu, q_uniform;
     int w_parity;             /* 0: w0 current, 1: w1 current (caller flips it by sweeps&1 after x-updates) */
     int fuse_pupdate;         /* 1: fuse p = r + beta p into the forward projector                      */
+    int defer_tv;             /* 1: admm_x_update skips the LAST sweep's TV pass; the caller runs admm_tv_pass
+                                 itself (lets the cut-edge exchange start before the TV kernel)         */
+    int reserved;
 } admm_state;
 
 /* One undirected edge (i<j) as seen by this rank; addresses are device pointers as integers. */
@@ -111,6 +114,7 @@ int admm_colnorm2(admm_plan* plan, float* d_img, long long stride, int node0, in
 /* same, HOST buffers (copies inside; one node) -- what `op(x).asarray()` costs a NumPy caller */
 int admm_forward_host(admm_plan* plan, int node, const float* h_img, float* h_sino);
 int admm_adjoint_host(admm_plan* plan, int node, const float* h_sino, float* h_img);
+int admm_colnorm2_host(admm_plan* plan, int node, float* h_img);
 
 /* ---- K6: rhs0_i = A^T P b_i + rho sum_j Q_ij (z_ij - y_ij,i)   block_6_admm_loop_ver2.py:87-95 ----------
  * nbr_* are device arrays over the CSR neighbour lists (G.neighbors(i) order): addresses of z_ij, of
