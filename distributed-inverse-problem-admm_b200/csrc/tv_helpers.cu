@@ -51,7 +51,8 @@ __global__ void normgrad_kernel(const double* __restrict__ x, int N, double eps,
         const int r = (int)(k / N), c = (int)(k % N);
         const double gx = (r < N - 1) ? x[k + N] - x[k] : 0.0;
         const double gy = (c < N - 1) ? x[k + 1] - x[k] : 0.0;
-        const double m = sqrt(gx * gx + gy * gy);
+        // no FMA contraction: NumPy rounds gx*gx, gy*gy and their sum separately
+        const double m = sqrt(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)));
         if (mag) mag[k] = m;
         if (px) {
             px[k] = (m > eps) ? gx / m : 0.0;

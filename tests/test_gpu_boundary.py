@@ -1,0 +1,155 @@
+"""The reference-named drop-in modules on the GPU: block_2 / block_3 / block_4 / block_5 / Gen_Sino_Partitioned, and the
+block_7-style call sequence, checked against the golden fixtures produced by the reference's own code and against the
+oracle."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "reference_golden.npz"))
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, dtype=np.float64).ravel() - np.asarray(b).ravel()) / np.linalg.norm(b))
+
+
+@pytest.mark.parametrize("N", [5, 16])
+def test_block4_helpers_bit_exact_vs_reference(N):
+    import block_4_tv_helpers as b4
+    import block_4_tv_helpers_with_plot as b4p
+    x, xf, px, py = GOLD[f"b4_N{N}_x"], GOLD[f"b4_N{N}_xf"], GOLD[f"b4_N{N}_px"], GOLD[f"b4_N{N}_py"]
+    gx, gy = b4._grad_forward_2d_from_vec(x, N)
+    assert np.array_equal(gx, GOLD[f"b4_N{N}_gx"]) and np.array_equal(gy, GOLD[f"b4_N{N}_gy"])
+    assert np.array_equal(b4._div_backward_2d_to_vec(px, py, N), GOLD[f"b4_N{N}_div"])
+    assert np.array_equal(b4.kt_subgrad_isotropic_tv_from_x(x, N), GOLD[f"b4_N{N}_kt"])
+    assert np.array_equal(b4.kt_subgrad_isotropic_tv_from_x(xf, N), GOLD[f"b4_N{N}_ktf"])
+    assert np.array_equal(b4p.edge_map_from_vector(x, N), GOLD[f"b4_N{N}_edge"])
+    assert np.array_equal(b4p.edge_map_from_vector(x, N, normalize=False), GOLD[f"b4_N{N}_edge_raw"])
+    # exact adjoint option: <Kx, p> == <x, K^T p>
+    kt = b4._div_backward_2d_to_vec(px, py, N, exact_adjoint=True)
+    assert abs(np.sum(gx * px + gy * py) - float(x @ kt)) < 1e-10
+    assert abs(b4.isotropic_tv_on_vector(x, N) - GOLD[f"b4_N{N}_edge_raw"].sum()) < 1e-12
+
+
+def test_block2_block3_gen_sino_against_oracle():
+    import block_2_load_odl_data as b2
+    import block_3_graph_and_precisions as b3
+    import Gen_Sino_Partitioned as gs
+    from oracle import oracle as O
+    N, V = 64, 5
+    data = b2.load_odl_data(N=N, num_nodes=V, noise_level=0.0, phantom_array=gs.ConstIm(N), make_plots=False)
+    for key in ("A_dense_list", "sinograms", "column_norms_all", "N", "num_nodes", "agg_ray_trafo", "A_agg",
+                "agg_sinogram", "agg_fbp_recon", "agg_ls_recon", "output_dir", "phantom", "phantoms"):
+        assert key in data
+    M = max(180, 3 * N)                                    # block_2_load_odl_data.py:31-33
+    per = O.angle_split(M, V)
+    thetas = O.node_angles(M, V)
+    assert [A.shape for A in data["A_dense_list"]] == [(m * N, N * N) for m in per]
+    for i in range(V):
+        ref = O.JosephOperator(N, thetas[i])
+        assert data["sinograms"][i].shape == (per[i], N)
+        assert _rel(data["sinograms"][i], ref.forward(gs.ConstIm(N))) < 1e-4
+        assert _rel(data["column_norms_all"][i], np.sqrt(ref.colnorm2())) < 1e-4
+    # aggregate operator == vstack of the node operators (contiguous partition)
+    agg = data["agg_ray_trafo"](data["agg_ray_trafo"].domain.element(gs.ConstIm(N))).asarray()
+    assert _rel(agg, np.vstack(data["sinograms"])) < 1e-6
+    # block_3 on operators
+    Wi, Q = b3.make_precisions(data["A_dense_list"], q_mode="harmonic")
+    Wo, Qo = O.make_precisions([O.JosephOperator(N, t).colnorm2() for t in thetas], "harmonic")
+    assert _rel(Wi[2], Wo[2]) < 1e-4 and _rel(Q(0, 3), Qo(0, 3)) < 1e-4
+    G, Wl, Qm, keep = b3.build_pixel_connected_Q_provider(A_dense_list=data["A_dense_list"], strategy="ring")
+    assert G.number_of_nodes() == V and keep is None
+    # generate_sinogram
+    noisy, rt, geom, space, A = gs.generate_sinogram(O.shepp_logan(48), np.zeros(30))
+    ref = O.JosephOperator(48, (np.arange(30) + 0.5) * np.pi / 30)
+    assert _rel(noisy.asarray(), ref.forward(O.shepp_logan(48))) < 1e-4 and A.shape == (30 * 48, 48 * 48)
+
+
+def test_block5_node_problem_reaches_the_minimiser():
+    from admm_b200 import RayTransformCUDA, node_angles
+    from block_5_node_problem import build_node_problem
+    from oracle import oracle as O
+    N, n = 32, 1024
+    th = node_angles(60, 2)[0]
+    ref = O.JosephOperator(N, th)
+    rng = np.random.default_rng(5)
+    b = ref.forward(O.shepp_logan(N)) + 0.01 * rng.standard_normal(ref.shape[0])
+    v = [O.shepp_logan(N).reshape(-1) + 0.1 * rng.standard_normal(n) for _ in range(2)]
+    q = [0.5 + rng.random(n) for _ in range(2)]
+    rho, lam = 2.0, 0.05
+    xi, prob = build_node_problem(RayTransformCUDA(N, th), b, rho, v, N, lam, q)
+    val = prob.solve(solver="SCS", eps=1e-6, max_iters=400, acceleration_lookback=20, verbose=False, warm_start=True)
+    assert prob.status in ("optimal", "optimal_inaccurate") and prob.solver_stats.num_iters > 0
+    # oracle minimiser of the same eq. (1)
+    x, d, w = np.zeros(n), np.zeros(2 * n), np.zeros(2 * n)
+    rhs0 = ref.adjoint(b) + rho * sum(qi * vi for qi, vi in zip(q, v))
+    for _ in range(300):
+        O.x_update(ref, 1.0, rhs0, rho * sum(q), rho, lam, 1, 12, x, d, w)
+    def F(xx):
+        return (0.5 * np.sum((ref.forward(xx) - b) ** 2) + lam * O.tv_canonical(xx, N)
+                + 0.5 * rho * sum(np.sum(qi * (xx - vi) ** 2) for qi, vi in zip(q, v)))
+    assert _rel(xi.value, x) < 2e-3
+    assert abs(val - F(x)) < 1e-3 * abs(F(x)) and abs(F(xi.value) - F(x)) < 1e-3 * abs(F(x))
+
+
+def test_block7_style_flow_runs_and_returns_reference_shaped_history():
+    """block_7_main_ver3.run_one_strategy's call sequence (:63-106) without its matplotlib figures."""
+    import block_2_load_odl_data as b2
+    import block_3_graph_and_precisions as b3
+    from block_6_admm_loop import decentralized_admm
+    from Gen_Sino_Partitioned import ConstIm
+    N, V = 32, 5
+    np.random.seed(0)
+    data = b2.load_odl_data(base_dir="unused", N=N, num_nodes=V, noise_level=0.005, phantom_array=ConstIm(N) / 400.0)
+    G, Wi_list, Qfn, keep = b3.build_pixel_connected_Q_provider(A_dense_list=data["A_dense_list"], strategy="knn", k=2,
+                                                                 seed=123, q_mode="arithmetic", verbose=False,
+                                                                 plot_union=True, show_plots=False)
+    assert keep.shape == (V, V, N * N)
+    x_list, hist = decentralized_admm(A_dense_list=data["A_dense_list"], sinograms=data["sinograms"], G=G,
+                                      Wi_list=Wi_list, Qij_diag_fn=Qfn, N=N, lam_tv=0.02, rho=2.0, max_iters=12,
+                                      max_inner_iters=100, eps_pri=1e-9, eps_dual=1e-9, verbose=False,
+                                      snapshot_dir=None, snapshot_every=3, snapshot_div=5,
+                                      phantom_true=data["phantom"], scs_total_iters=100, scs_chunk_iters=20)
+    assert np.stack(x_list).shape == (V, N * N) and x_list[0].reshape(N, N).shape == (N, N)
+    for key in ("primal", "dual", "pri_per_node", "dual_per_node", "obj_per_node", "obj_total", "mse_sino_per_node",
+                "mse_sino_total", "img_mse_per_node", "img_mse_total", "g_norm_history", "eps_used_history",
+                "eps_target_history", "primal_res", "dual_res", "obj"):
+        assert len(hist[key]) == 12, key
+    assert hist["pri_per_node"][0].shape == (V,) and hist["primal"][-1] < hist["primal"][0]
+    assert hist["img_mse_total"][-1] < hist["img_mse_total"][0]
+
+
+def test_full_size_properties_2048():
+    """BASELINE cfg-4 geometry (2048^2, 720 angles over 64 nodes): size-independent properties of the operator pair."""
+    import torch
+    from admm_b200 import Plan, node_angles
+    N, M, V = 2048, 720, 64
+    plan = Plan(N, node_angles(M, V))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand(V, N * N, device="cuda", generator=g)
+    y = torch.rand(plan.A, N, device="cuda", generator=g)
+    Ax, Aty = torch.zeros(plan.A, N, device="cuda"), torch.zeros(V, N * N, device="cuda")
+    plan.forward(x, Ax)
+    plan.adjoint(y, Aty)
+    lhs, rhs = float((Ax.double() * y.double()).sum()), float((x.double() * Aty.double()).sum())
+    assert abs(lhs - rhs) < 2e-6 * abs(lhs)                      # <Ax, y> == <x, A^T y>
+    x2 = torch.rand(V, N * N, device="cuda", generator=g)
+    A2, A12 = torch.zeros_like(Ax), torch.zeros_like(Ax)
+    plan.forward(x2, A2)
+    plan.forward(x + 2.0 * x2, A12)
+    assert float((A12 - (Ax + 2.0 * A2)).norm() / A12.norm()) < 1e-5   # linearity
+    ones = torch.ones(1, N * N, device="cuda").repeat(V, 1)
+    plan.forward(ones, Ax)
+    th = np.concatenate(node_angles(M, V))
+    s = -1 + (np.arange(N) + 0.5) * 2 / N
+    c, sn = np.abs(np.cos(th))[:, None], np.abs(np.sin(th))[:, None]
+    # chord length of [-1,1]^2 along the ray (theta, s)
+    a, b = np.maximum(c, sn), np.minimum(c, sn)
+    smax, sflat = a + b, a - b
+    chord = np.where(np.abs(s)[None, :] <= sflat, 2.0 / a, np.clip((smax - np.abs(s)[None, :]) / (a * np.maximum(b, 1e-12)), 0, None))
+    got = Ax.cpu().numpy()
+    assert np.linalg.norm(got - chord) / np.linalg.norm(chord) < 2e-3
+    plan.close()
