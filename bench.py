@@ -38,6 +38,9 @@ CONFIGS = {
                  desc="1024x1024, 720 angles, 32 nodes, heterogeneous noise precisions (weighted LS), block_3 arithmetic Q"),
     "cfg4": dict(N=2048, M=720, V=64, graph="er", hetero=False, wq=False,
                  desc="Shepp-Logan 2048x2048, 720 angles, 64 nodes, connected Erdos-Renyi(p=0.1) graph, uniform precisions"),
+    # configs[4]: slice-parallel batch = disjoint union of per-slice graphs; batch dimension = slice x node
+    "cfg5": dict(N=512, M=360, V=16, graph="regular", hetero=False, wq=False, slices=256,
+                 desc="batched 256 slices of 512x512 (slice-parallel), 360 angles, 16 nodes each on a 4-regular graph"),
 }
 LAM, RHO, SIGMA = 0.02, 2.0, 0.005  # block_7_main_ver3.py:336-337,342
 METRIC = "ADMM iters/sec (all nodes)"
@@ -46,10 +49,28 @@ METRIC = "ADMM iters/sec (all nodes)"
 def make_graph(cfg):
     from admm_b200 import make_graph as mg
     if cfg["graph"] == "ring":
-        return mg("ring", cfg["V"])
-    if cfg["graph"] == "regular":
-        return mg("regular", cfg["V"], seed=0, degree=4)
-    return mg("er", cfg["V"], seed=0, p=0.1)
+        G = mg("ring", cfg["V"])
+    elif cfg["graph"] == "regular":
+        G = mg("regular", cfg["V"], seed=0, degree=4)
+    else:
+        G = mg("er", cfg["V"], seed=0, p=0.1)
+    S = cfg.get("slices", 1)
+    if S > 1:   # slice-parallel: S independent copies, node ids slice*V + i
+        import networkx as nx
+        H = nx.Graph()
+        V = cfg["V"]
+        for s in range(S):
+            H.add_nodes_from(range(s * V, (s + 1) * V))
+        for s in range(S):
+            for i in range(V):                       # keep each copy's adjacency (neighbour) order
+                for j in G.neighbors(i):
+                    H.add_edge(s * V + i, s * V + j)
+        return H
+    return G
+
+
+def total_nodes(cfg):
+    return cfg["V"] * cfg.get("slices", 1)
 
 
 def node_sigma(cfg, i):
@@ -59,7 +80,7 @@ def node_sigma(cfg, i):
 def node_prec(cfg):
     if not cfg["hetero"]:
         return None
-    s = np.array([node_sigma(cfg, i) for i in range(cfg["V"])])
+    s = np.array([node_sigma(cfg, i) for i in range(total_nodes(cfg))])
     return (s ** -2) / np.max(s ** -2)
 
 
@@ -72,8 +93,9 @@ def synth_gpu(cfg, device):
     operator (input synthesis only)."""
     import torch
     from admm_b200 import Plan, node_angles, shepp_logan
-    N, M, V = cfg["N"], cfg["M"], cfg["V"]
-    thetas = node_angles(M, V)
+    N, M = cfg["N"], cfg["M"]
+    thetas = node_angles(M, cfg["V"]) * cfg.get("slices", 1)
+    V = len(thetas)
     img = shepp_logan(N).astype(np.float32)
     plan = Plan(N, thetas, device=device)
     d_img = torch.from_numpy(np.ascontiguousarray(img.reshape(1, -1))).to(f"cuda:{device}").repeat(V, 1)
@@ -103,10 +125,10 @@ def q_provider(Wl):
 
 def algorithmic_bytes(cfg, G, S, C, nonuniform_q):
     """BASELINE.md section 5 per outer iteration (fp32)."""
-    N, M, V = cfg["N"], cfg["M"], cfg["V"]
+    N, M, V = cfg["N"], cfg["M"], total_nodes(cfg)
     from admm_b200 import angle_split
     n = N * N
-    per = angle_split(M, V)
+    per = angle_split(M, cfg["V"]) * cfg.get("slices", 1)
     E = G.number_of_edges()
     tot = 0
     for i in range(V):
@@ -167,12 +189,13 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 def cpu_sample(cfg, S, C, budget_s, steps=1, warmup=0):
     from oracle import oracle as O
-    N, M, V = cfg["N"], cfg["M"], cfg["V"]
+    N, M = cfg["N"], cfg["M"]
     n = N * N
-    G = O.make_graph(cfg["graph"] if cfg["graph"] != "regular" else "regular", V, seed=0, p=0.1, degree=4)
+    G = make_graph(cfg)
+    V = G.number_of_nodes()
     edges, ptr, nidx, nedge, nend = O.graph_csr(G)
     E = len(edges)
-    thetas = O.node_angles(M, V)
+    thetas = O.node_angles(M, cfg["V"]) * cfg.get("slices", 1)
     img = O.shepp_logan(N)
     cores = O.num_threads()
     prec = node_prec(cfg)
@@ -241,7 +264,7 @@ def run_reference(args, cfg, rank):
 
 
 def workload_config(args, cfg, G):
-    c = {"workload": f"{args.config}: {cfg['desc']}", "N": cfg["N"], "angles": cfg["M"], "nodes": cfg["V"],
+    c = {"workload": f"{args.config}: {cfg['desc']}", "N": cfg["N"], "angles": cfg["M"], "nodes": total_nodes(cfg),
          "graph": cfg["graph"], "lam_tv": LAM, "rho": RHO, "tv_mu": RHO, "tv_sweeps": args.tv_sweeps,
          "cg_iters": args.cg_iters, "noise_sigma": SIGMA, "partition": "contiguous",
          "inputs_larger_than_L2": True, "stop_test": "disabled in the timed region"}
@@ -260,12 +283,16 @@ def main():
     ap.add_argument("--cg-iters", type=int, default=8)
     ap.add_argument("--tv-sweeps", type=int, default=1)
     ap.add_argument("--node-group", type=int, default=0)
+    ap.add_argument("--slices", type=int, default=0, help="override the slice count of cfg5")
     ap.add_argument("--no-fuse", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="no per-kernel CUDA events in the timed region")
     args = ap.parse_args()
-    cfg = CONFIGS[args.config]
+    cfg = dict(CONFIGS[args.config])
+    if args.slices and "slices" in cfg:
+        cfg["slices"] = args.slices
+        cfg["desc"] = cfg["desc"].replace("256 slices", f"{args.slices} slices")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

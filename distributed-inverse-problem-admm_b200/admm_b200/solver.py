@@ -39,7 +39,7 @@ class ADMMEngine:
     def __init__(self, thetas, sinograms, G, N, D=None, det_w=2.0, lam_tv=0.01, rho=1.0, Q=None, Wi_list=None,
                  node_prec=None, tv_mu=None, tv_sweeps=1, cg_iters=8, phantom_true=None, weighted_z=False,
                  device=0, dist=None, rank=0, world=1, group=None, node_group=None, fuse_pupdate=True,
-                 max_iters=200):
+                 max_iters=200, ax_refresh_every=10):
         torch = _torch()
         nat.require_cuda()
         self.torch = torch
@@ -63,6 +63,7 @@ class ADMMEngine:
         self.plan = Plan(N, [thetas[g] for g in self.loc], self.D, det_w, device)
         A = self.A = self.plan.A
         self.node_group = int(node_group) if node_group else V
+        self.ax_refresh_every = max(1, int(ax_refresh_every))
 
         # ---- data ------------------------------------------------------------------------------------
         b = np.concatenate([np.asarray(sinograms[g], dtype=np.float32).reshape(-1, self.D) for g in self.loc], axis=0)
@@ -244,6 +245,8 @@ class ADMMEngine:
         sharded the last TV pass is deferred (see step) so the exchange can start as soon as x is final."""
         L, h, st = nat.lib(), self.plan.handle, self.st
         sref = ctypes.byref(st)
+        # A x is carried by the CG recurrence (ax += alpha A p); it is re-projected every `ax_refresh_every` iterations
+        st.reuse_ax = 0 if (self.k % self.ax_refresh_every == 0) else 1
         nat.check(L.admm_rhs0(h, sref, self.nbr_ptr.data_ptr(), self.nbr_z.data_ptr(), self.nbr_y.data_ptr(),
                               self.nbr_q.data_ptr(), 0, self.V, self._stream()), "admm_rhs0")
         for n0 in range(0, self.V, self.node_group):

@@ -48,7 +48,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                        # --- B200 solver controls (not in the reference) ---
                        cg_iters=8, tv_sweeps=1, tv_mu=None, node_prec=None, weighted_z=False, scs_eps=None,
                        check_every=1, node_group=None, fuse_pupdate=True, device=None, return_engine=False,
-                       distributed=None,
+                       distributed=None, ax_refresh_every=10,
                        **kwargs):
     """Returns x_per_node as list of reconstructions, each length n, and the history of residual norms
     (block_6_admm_loop_ver2.py:21-24).
@@ -93,7 +93,8 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                      Wi_list=Wi_list, node_prec=node_prec, tv_mu=tv_mu, tv_sweeps=tv_sweeps,
                      cg_iters=min(int(cg_iters), int(max_inner_iters)), phantom_true=phantom_true,
                      weighted_z=weighted_z, device=device, dist=dist if world > 1 else None, rank=rank, world=world,
-                     group=group, node_group=node_group, fuse_pupdate=fuse_pupdate, max_iters=max_iters)
+                     group=group, node_group=node_group, fuse_pupdate=fuse_pupdate, max_iters=max_iters,
+                     ax_refresh_every=ax_refresh_every)
     eng._node_prec_all = node_prec
 
     print(f"Max ADMM Iteration in Block-6 B4 Loop = {max_iters}") if verbose else None

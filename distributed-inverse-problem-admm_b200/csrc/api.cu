@@ -384,11 +384,11 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
     int parity = s->w_parity;  // the caller flips st->w_parity (sweeps & 1) once every node group is done
     for (int sw = 0; sw < sweeps; ++sw) {
         // r = rhs0 + tvterm - H x ; p = r ; rr -> S_RR0 ; ax = A x
-        FwdParams F = make_fwd(p, s->x + off, s->stride, node0);
-        CK(launch_forward(F, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
-        SP.mode = 0;
-        CK(launch_sino_axpy(SP, st));
-        BackParams B = make_back(p, s->q, s->prec, s->r + off, s->stride, node0);
+        if (!(s->reuse_ax || sw > 0)) {   // later sweeps: ax is current by the recurrence
+            FwdParams F = make_fwd(p, s->x + off, s->stride, node0);
+            CK(launch_forward(F, nodes, p->max_chunks, make_red(p, s->ax, node0, nodes), st));
+        }
+        BackParams B = make_back(p, s->ax, s->prec, s->r + off, s->stride, node0);
         B.v = s->x + off; B.rhoD_vec = s->rhoD_vec ? s->rhoD_vec + off : nullptr; B.rhoD_s = s->rhoD_s; B.mu = s->mu;
         B.rhs0 = s->rhs0 + off; B.tvterm = s->tvterm + off; B.p_out = s->p0 + off;
         B.part = part; B.counter = counter; B.scal = s->scal; B.dot_slot = S_RR0;

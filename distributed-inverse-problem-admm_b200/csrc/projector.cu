@@ -209,8 +209,8 @@ fwd_strip_kernel(const FwdParams P) {
 
 __global__ void __launch_bounds__(256)
 fwd_reduce_kernel(const FwdReduceParams P) {
-    const int aid = P.A0 + blockIdx.y;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int aid = P.A0 + blockIdx.x;          // angle rows on grid.x (can exceed 65535 in slice-batched runs)
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= P.D) return;
     const int* __restrict__ js = P.jstart + (long long)aid * P.nRec;
     const float* __restrict__ rc = P.recs + (long long)aid * P.nRec * P.span;
@@ -447,8 +447,8 @@ cudaError_t launch_forward(const FwdParams& P, int nodes, int max_chunks, const 
     }
     dim3 grid(P.nTi * P.nSeg * max_chunks, nodes, 2);
     { ProfScope ps(P.r ? KC_FWD_FUSED : KC_FWD, st); fwd_strip_kernel<<<grid, FTHREADS, smem, st>>>(P); }
-    dim3 rgrid((R.D + 255) / 256, R.A1 - R.A0);
-    if (rgrid.y > 0) { ProfScope ps(KC_FWD_REDUCE, st); fwd_reduce_kernel<<<rgrid, 256, 0, st>>>(R); }
+    dim3 rgrid(R.A1 - R.A0, (R.D + 255) / 256);
+    if (rgrid.x > 0) { ProfScope ps(KC_FWD_REDUCE, st); fwd_reduce_kernel<<<rgrid, 256, 0, st>>>(R); }
     return cudaGetLastError();
 }
 

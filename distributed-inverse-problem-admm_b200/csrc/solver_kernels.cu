@@ -260,7 +260,7 @@ p_update_kernel(const CgParams P) {
 // Ax += alpha(node) * q on sinogram rows (keeps A x current without an extra projection; block_6_ver2:190-194)
 __global__ void __launch_bounds__(256)
 sino_axpy_kernel(const SinoParams P) {
-    const int a = P.A0 + blockIdx.y;
+    const int a = P.A0 + blockIdx.x;            // angle rows on grid.x
     const int node = P.anode[a];
     const double* sc = P.scal + (long long)node * NSCAL;
     float alpha = 1.f;
@@ -268,7 +268,7 @@ sino_axpy_kernel(const SinoParams P) {
         const double php = sc[S_PHP], rr = sc[P.rr_in];
         alpha = (php > 0.0) ? (float)(rr / php) : 0.f;
     }
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P.D; j += gridDim.x * blockDim.x) {
+    for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < P.D; j += gridDim.y * blockDim.x) {
         const long long g = (long long)a * P.D + j;
         P.ax[g] = (P.mode == 0) ? P.q[g] : fmaf(alpha, P.q[g], P.ax[g]);
     }
@@ -493,7 +493,7 @@ cudaError_t launch_p_update(const CgParams& P, int nodes, cudaStream_t st) {
 }
 cudaError_t launch_sino_axpy(const SinoParams& P, cudaStream_t st) {
     if (P.A1 <= P.A0) return cudaSuccess;
-    { ProfScope ps(KC_SINO_AXPY, st); sino_axpy_kernel<<<dim3((P.D + 255) / 256, P.A1 - P.A0), 256, 0, st>>>(P); }
+    { ProfScope ps(KC_SINO_AXPY, st); sino_axpy_kernel<<<dim3(P.A1 - P.A0, (P.D + 255) / 256), 256, 0, st>>>(P); }
     return cudaGetLastError();
 }
 cudaError_t launch_sino_resid(const SinoParams& P, int nodes, cudaStream_t st) {

@@ -68,7 +68,8 @@ typedef struct admm_state {
     int fuse_pupdate;         /* 1: fuse p = r + beta p into the forward projector                      */
     int defer_tv;             /* 1: admm_x_update skips the LAST sweep's TV pass; the caller runs admm_tv_pass
                                  itself (lets the cut-edge exchange start before the TV kernel)         */
-    int reserved;
+    int reuse_ax;             /* 1: admm_x_update takes A x from `ax` (kept current by the CG recurrence) instead of
+                                 re-projecting x for the warm-start residual; set 0 periodically to refresh   */
 } admm_state;
 
 /* One undirected edge (i<j) as seen by this rank; addresses are device pointers as integers. */
