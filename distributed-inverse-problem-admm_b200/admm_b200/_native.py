@@ -19,7 +19,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 NSCAL = 16
-S_RR0, S_RR1, S_PHP, S_TV, S_GN2, S_IMG, S_MSE = range(7)
+S_RR0, S_RR1, S_PHP, S_RHP, S_HPHP, S_TV, S_GN2, S_IMG, S_MSE = range(9)
 INFO_N, INFO_D, INFO_V, INFO_A, INFO_PART_FLOATS, INFO_FWD_SPAN, INFO_FWD_NREC, INFO_BACK_SPAN, INFO_WS_BYTES = range(9)
 
 
@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 class State(ctypes.Structure):
     """struct admm_state (include/admm_b200.h)."""
     _fields_ = [(k, ctypes.c_void_p) for k in
-                ("x", "r", "p0", "p1", "hp", "rhs0", "tvterm", "atb", "w0", "w1", "rhoD_vec", "rhoD_s", "prec",
+                ("x", "r", "r1", "p0", "p1", "hp", "rhs0", "tvterm", "atb", "w0", "w1", "rhoD_vec", "rhoD_s", "prec",
                  "xtrue", "q", "ax", "b", "scal", "part", "counter")] + [
         ("stride", ctypes.c_longlong), ("rho", ctypes.c_float), ("lam", ctypes.c_float), ("mu", ctypes.c_float),
         ("q_uniform", ctypes.c_float), ("w_parity", ctypes.c_int), ("fuse_pupdate", ctypes.c_int),

@@ -113,6 +113,7 @@ class ADMMEngine:
         # ---- state ---------------------------------------------------------------------------------------
         z = lambda *s: torch.zeros(*s, **f32)  # noqa: E731
         self.x, self.r, self.p0, self.p1, self.hp = z(V, n), z(V, n), z(V, n), z(V, n), z(V, n)
+        self.r1 = z(V, n)
         self.rhs0, self.tvterm = z(V, n), z(V, n)
         self.w0, self.w1 = z(V, 2, n), z(V, 2, n)
         self.q, self.ax = z(A, self.D), z(A, self.D)
@@ -224,7 +225,7 @@ class ADMMEngine:
 
     def _fill_state(self, fuse):
         st = self.st
-        for name in ("x", "r", "p0", "p1", "hp", "rhs0", "tvterm", "atb", "w0", "w1", "q", "ax", "b", "scal", "part",
+        for name in ("x", "r", "r1", "p0", "p1", "hp", "rhs0", "tvterm", "atb", "w0", "w1", "q", "ax", "b", "scal", "part",
                      "counter", "rhoD_s"):
             setattr(st, name, getattr(self, name).data_ptr())
         st.rhoD_vec = self.rhoD_vec.data_ptr() if self.rhoD_vec is not None else None
@@ -233,7 +234,7 @@ class ADMMEngine:
         st.stride = self.n
         st.rho, st.lam, st.mu, st.q_uniform = self.rho, self.lam, self.mu, self.q_uniform
         st.w_parity = 0
-        st.fuse_pupdate = 1 if fuse else 0
+        st.fuse_pupdate = int(fuse) if not isinstance(fuse, bool) else (2 if fuse else 0)
         st.defer_tv = 1 if self.world > 1 else 0
 
     def _stream(self):
@@ -430,6 +431,7 @@ class NodeProblem:
         self.deg = deg
         z = lambda *s: torch.zeros(*s, **f32)  # noqa: E731
         self.x, self.r, self.p0, self.p1, self.hp = z(1, n), z(1, n), z(1, n), z(1, n), z(1, n)
+        self.r1 = z(1, n)
         self.rhs0, self.tvterm = z(1, n), z(1, n)
         self.w0, self.w1 = z(1, 2, n), z(1, 2, n)
         self.q, self.ax = z(self.plan.A, self.D), z(self.plan.A, self.D)
@@ -439,12 +441,12 @@ class NodeProblem:
         self.rhoD_vec = (self.rho * self.qv[:deg].sum(dim=0)).reshape(1, n).contiguous() if deg else z(1, n)
         self.rhoD_s = z(1)
         st = self.st = nat.State()
-        for name in ("x", "r", "p0", "p1", "hp", "rhs0", "tvterm", "atb", "w0", "w1", "q", "ax", "b", "scal", "part",
+        for name in ("x", "r", "r1", "p0", "p1", "hp", "rhs0", "tvterm", "atb", "w0", "w1", "q", "ax", "b", "scal", "part",
                      "counter", "rhoD_s", "rhoD_vec", "prec"):
             setattr(st, name, getattr(self, name).data_ptr())
         st.xtrue = None
         st.stride, st.rho, st.lam, st.mu, st.q_uniform = n, self.rho, self.lam, self.mu, 1.0
-        st.w_parity, st.fuse_pupdate = 0, 1
+        st.w_parity, st.fuse_pupdate = 0, 2
         ptr = torch.tensor([0, deg], dtype=torch.int32, device=self.dev)
         a = lambda t, k: t.data_ptr() + k * n * 4  # noqa: E731
         i64 = lambda v: torch.tensor(v if v else [0], dtype=torch.int64, device=self.dev)  # noqa: E731

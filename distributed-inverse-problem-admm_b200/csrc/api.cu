@@ -239,7 +239,8 @@ static FwdParams make_fwd(const admm_plan* p, const float* img, long long stride
     P.img = img; P.img_stride = stride; P.ang = p->d_ang; P.optr = p->d_optr; P.oidx = p->d_oidx;
     P.recs = p->d_recs; P.jstart = p->d_jstart; P.V = p->V; P.node0 = node0; P.N = p->N; P.D = p->D;
     P.nTi = p->nTi; P.nSeg = p->nSeg; P.span = p->span; P.seg = p->seg;
-    P.r = nullptr; P.p_out = nullptr; P.scal = nullptr; P.beta_num = 0; P.beta_den = 0;
+    P.r = nullptr; P.p_out = nullptr; P.scal = nullptr; P.beta_num = 0; P.beta_den = 0; P.mode = 0;
+    P.hp = nullptr; P.x_io = nullptr; P.r_out = nullptr; P.part = nullptr; P.counter = nullptr; P.rr_out = 0;
     return P;
 }
 
@@ -394,44 +395,57 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
         B.part = part; B.counter = counter; B.scal = s->scal; B.dot_slot = S_RR0;
         CK(launch_back(BACK_RESID0, B, nodes, st));
         int cur = 0;
+        float* rcur = s->r + off;            // residual buffer currently holding r (fuse 2 ping-pongs r / r1)
         for (int it = 0; it < cg_iters; ++it) {
             const int rr_in = (it & 1) ? S_RR1 : S_RR0, rr_out = (it & 1) ? S_RR0 : S_RR1;
             float* pcur = (cur ? s->p1 : s->p0) + off;
             float* poth = (cur ? s->p0 : s->p1) + off;
-            if (it > 0) {
-                if (s->fuse_pupdate) {
-                    FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
-                    Fp.r = s->r + off; Fp.p_out = poth; Fp.scal = s->scal; Fp.beta_num = rr_in; Fp.beta_den = rr_out;
-                    CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
-                    cur ^= 1;
-                    pcur = poth;
-                } else {
-                    CgParams U{};
-                    U.r = s->r + off; U.p = pcur; U.p_out = poth; U.stride = s->stride; U.n = n; U.node0 = node0;
-                    U.rr_in = rr_out; U.rr_out = rr_in;  // beta = scal[rr_in(it)] / scal[rr_out(it)] = new / old
-                    U.scal = s->scal;
-                    CK(launch_p_update(U, nodes, st));
-                    cur ^= 1;
-                    pcur = poth;
-                    FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
-                    CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
-                }
+            if (it > 0 && s->fuse_pupdate == 2) {
+                // x += alpha p ; r' = r - alpha Hp ; p' = r' + beta p ; <r',r'> -> rr_in  -- all inside the projector
+                float* roth = (rcur == s->r + off) ? s->r1 + off : s->r + off;
+                FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
+                Fp.mode = 2; Fp.r = rcur; Fp.r_out = roth; Fp.p_out = poth; Fp.hp = s->hp + off; Fp.x_io = s->x + off;
+                Fp.scal = s->scal; Fp.beta_den = rr_out /* slot of the previous <r,r> */; Fp.rr_out = rr_in;
+                Fp.part = part; Fp.counter = counter;
+                CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
+                cur ^= 1; pcur = poth; rcur = roth;
+            } else if (it > 0 && s->fuse_pupdate == 1) {
+                FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
+                Fp.mode = 1; Fp.r = s->r + off; Fp.p_out = poth; Fp.scal = s->scal; Fp.beta_num = rr_in; Fp.beta_den = rr_out;
+                CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
+                cur ^= 1; pcur = poth;
+            } else if (it > 0) {
+                CgParams U{};
+                U.r = s->r + off; U.p = pcur; U.p_out = poth; U.stride = s->stride; U.n = n; U.node0 = node0;
+                U.rr_in = rr_out; U.rr_out = rr_in;  // beta = scal[rr_in(it)] / scal[rr_out(it)] = new / old
+                U.scal = s->scal;
+                CK(launch_p_update(U, nodes, st));
+                cur ^= 1; pcur = poth;
+                FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
+                CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
             } else {
                 FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
                 CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
             }
             BackParams H = make_back(p, s->q, s->prec, s->hp + off, s->stride, node0);
             H.v = pcur; H.rhoD_vec = B.rhoD_vec; H.rhoD_s = s->rhoD_s; H.mu = s->mu;
+            H.rvec = (s->fuse_pupdate == 2) ? rcur : nullptr;
             H.part = part; H.counter = counter; H.scal = s->scal; H.dot_slot = S_PHP;
             CK(launch_back(BACK_HP, H, nodes, st));
             SP.mode = 1; SP.rr_in = rr_in;
             CK(launch_sino_axpy(SP, st));
-            CgParams U{};
-            U.x = s->x + off; U.r = s->r + off; U.p = pcur; U.hp = s->hp + off; U.stride = s->stride; U.n = n;
-            U.node0 = node0; U.rr_in = rr_in; U.rr_out = rr_out; U.part = part; U.counter = counter; U.scal = s->scal;
-            long long nb = (n / 4 + 256 * 4 - 1) / (256 * 4);
-            nb = std::max(1LL, std::min(nb, 4096LL));
-            CK(launch_cg_update(U, nodes, (int)nb, st));
+            const bool last = (it == cg_iters - 1);
+            if (s->fuse_pupdate != 2 || last) {
+                // separate vector update (every iteration when unfused; once, after the last one, when fused):
+                // the final residual always lands in s->r
+                CgParams U{};
+                U.x = s->x + off; U.r = s->r + off; U.r_in = rcur; U.p = pcur; U.hp = s->hp + off; U.stride = s->stride;
+                U.n = n; U.node0 = node0; U.rr_in = rr_in; U.rr_out = rr_out; U.part = part; U.counter = counter;
+                U.scal = s->scal;
+                long long nb = (n / 4 + 256 * 4 - 1) / (256 * 4);
+                nb = std::max(1LL, std::min(nb, 4096LL));
+                CK(launch_cg_update(U, nodes, (int)nb, st));
+            }
         }
         if (!(s->defer_tv && sw == sweeps - 1)) {
             CK(launch_tv(make_tv(p, s, node0, true, parity), nodes, st));

@@ -62,20 +62,76 @@ fwd_strip_kernel(const FwdParams P) {
         s_ang[tid] = make_float4(r.inv_major, r.slope, r.inv_slope, 0.f);
     }
 
-    // fused CG direction update p_new = r + beta p_old
-    float beta = 0.f;
+    // fused CG vector updates (see FwdParams): mode 1: p' = r + beta p ; mode 2: x += alpha p, r' = r - alpha Hp,
+    // p' = r' + beta p.  Exactly one (orientation, chunk) pass per pixel -- the "writer" -- stores the results.
+    __shared__ __align__(16) float red[64];
+    float beta = 0.f, alpha = 0.f, rsum = 0.f;
+    const int mode = P.mode;
     const float* __restrict__ rimg = nullptr;
+    const float* __restrict__ hpimg = nullptr;
     float* pout = nullptr;
-    if (P.r != nullptr) {
-        const double den = P.scal[(long long)node * NSCAL + P.beta_den];
-        const double num = P.scal[(long long)node * NSCAL + P.beta_num];
-        beta = (den > 0.0) ? (float)(num / den) : 0.f;
-        rimg = P.r + (long long)blockIdx.y * P.img_stride;
-        // exactly one (orientation, chunk) pass per pixel writes p_new: the first non-empty orientation, chunk 0
+    float* xio = nullptr;
+    float* rout = nullptr;
+    bool writer = false;
+    if (mode != 0) {
+        const double* sc = P.scal + (long long)node * NSCAL;
+        if (mode == 1) {
+            const double den = sc[P.beta_den], num = sc[P.beta_num];
+            beta = (den > 0.0) ? (float)(num / den) : 0.f;
+        } else {
+            // <r',r'> = rr - 2 alpha <r,Hp> + alpha^2 <Hp,Hp>, and <r,Hp> = <p,Hp> for CG directions (p - r is a
+            // multiple of the previous direction, which is H-conjugate to p), so  rr' = alpha^2 <Hp,Hp> - rr.
+            const double rr = sc[P.beta_den], php = sc[S_PHP], hh = sc[S_HPHP];
+            const double al = (php > 0.0) ? rr / php : 0.0;
+            const double rr_est = al * al * hh - rr;
+            alpha = (float)al;
+            beta = (rr > 0.0) ? (float)fmax(0.0, rr_est / rr) : 0.f;
+        }
+        const long long off = (long long)blockIdx.y * P.img_stride;
+        rimg = P.r + off;
         const int x_has = P.optr[node + 1] - P.optr[node];
-        const bool writer = (ch == 0) && (xdom ? true : (x_has == 0));
-        pout = writer ? (P.p_out + (long long)blockIdx.y * P.img_stride) : nullptr;
+        writer = (ch == 0) && (xdom ? true : (x_has == 0));
+        if (writer) pout = P.p_out + off;
+        if (mode == 2) {
+            hpimg = P.hp + off;
+            if (writer) { xio = P.x_io + off; rout = P.r_out + off; }
+        }
     }
+    // p_old (and r, Hp, x) at flat index g -> the value to project; stores the updates when this block is the writer
+    auto fuse1 = [&](long long g, float pold) -> float {
+        if (mode == 0) return pold;
+        float rv = rimg[g];
+        if (mode == 2) {
+            rv = fmaf(-alpha, hpimg[g], rv);
+            if (writer) { xio[g] = fmaf(alpha, pold, xio[g]); rout[g] = rv; rsum = fmaf(rv, rv, rsum); }
+        }
+        const float pn = fmaf(beta, pold, rv);
+        if (writer) pout[g] = pn;
+        return pn;
+    };
+    auto fuse4 = [&](long long g, float4 pold) -> float4 {
+        if (mode == 0) return pold;
+        float4 rv = ld4(rimg + g);
+        if (mode == 2) {
+            const float4 hv = ld4(hpimg + g);
+            rv.x = fmaf(-alpha, hv.x, rv.x); rv.y = fmaf(-alpha, hv.y, rv.y);
+            rv.z = fmaf(-alpha, hv.z, rv.z); rv.w = fmaf(-alpha, hv.w, rv.w);
+            if (writer) {
+                float4 xv = ld4(xio + g);
+                xv.x = fmaf(alpha, pold.x, xv.x); xv.y = fmaf(alpha, pold.y, xv.y);
+                xv.z = fmaf(alpha, pold.z, xv.z); xv.w = fmaf(alpha, pold.w, xv.w);
+                st4(xio + g, xv);
+                st4(rout + g, rv);
+                rsum = fmaf(rv.x, rv.x, rsum); rsum = fmaf(rv.y, rv.y, rsum);
+                rsum = fmaf(rv.z, rv.z, rsum); rsum = fmaf(rv.w, rv.w, rsum);
+            }
+        }
+        float4 pn;
+        pn.x = fmaf(beta, pold.x, rv.x); pn.y = fmaf(beta, pold.y, rv.y);
+        pn.z = fmaf(beta, pold.z, rv.z); pn.w = fmaf(beta, pold.w, rv.w);
+        if (writer) st4(pout + g, pn);
+        return pn;
+    };
 
     const int slot = tid / FTPA, t = tid % FTPA;
     const int nslab = (Kseg + FL - 1) / FL;
@@ -103,21 +159,11 @@ fwd_strip_kernel(const FwdParams P) {
                 if (u < Wt) {
                     const long long g = (long long)(U0 + u) * N + K0 + k4;
                     if (k4 + 3 < Lt && ((N & 3) == 0)) {
-                        val = ld4(img + g);
-                        if (rimg) {
-                            const float4 rv = ld4(rimg + g);
-                            val.x = fmaf(beta, val.x, rv.x); val.y = fmaf(beta, val.y, rv.y);
-                            val.z = fmaf(beta, val.z, rv.z); val.w = fmaf(beta, val.w, rv.w);
-                            if (pout) st4(pout + g, val);
-                        }
+                        val = fuse4(g, ld4(img + g));
                     } else {
                         float tmp[4] = {0.f, 0.f, 0.f, 0.f};
                         for (int i = 0; i < 4; ++i)
-                            if (k4 + i < Lt) {
-                                float x = img[g + i];
-                                if (rimg) { x = fmaf(beta, x, rimg[g + i]); if (pout) pout[g + i] = x; }
-                                tmp[i] = x;
-                            }
+                            if (k4 + i < Lt) tmp[i] = fuse1(g + i, img[g + i]);
                         val = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
                     }
                 }
@@ -131,8 +177,7 @@ fwd_strip_kernel(const FwdParams P) {
                 float x = 0.f;
                 if (k < Lt && u < Wt) {
                     const long long g = (long long)(K0 + k) * N + U0 + u;
-                    x = img[g];
-                    if (rimg) { x = fmaf(beta, x, rimg[g]); if (pout) pout[g] = x; }
+                    x = fuse1(g, img[g]);
                 }
                 S[k * FPITCH + FHALO + u] = x;
             }
@@ -205,6 +250,12 @@ fwd_strip_kernel(const FwdParams P) {
         P.recs[((long long)s_aid[ai] * nRec + rec) * span + k] = acc_s[i];
     }
     if (tid < na) P.jstart[(long long)s_aid[tid] * nRec + rec] = s_jseg[tid];
+    if (mode == 2 && writer) {   // block-uniform: exact <r', r'> of this node over its nTi*nSeg writer blocks
+        float v[1] = {rsum};
+        block_sum<1>(v, red);
+        grid_reduce_store<1>(v, P.part + (long long)blockIdx.y * nRec, P.counter + blockIdx.y, rec, nRec,
+                             P.scal + (long long)node * NSCAL + P.rr_out, red);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -239,7 +290,7 @@ back_tile_kernel(const BackParams P) {
     unsigned* s_qa = reinterpret_cast<unsigned*>(s_c + BAC);  // [BAC] biased shared-window address of each window
     int* s_jw = reinterpret_cast<int*>(s_qa + BAC);           // [BAC] first detector bin of each window
     float* s_sc = reinterpret_cast<float*>(s_jw + BAC);       // [BAC] window scale (step weight * precision)
-    __shared__ float red[64];
+    __shared__ __align__(16) float red[96];
 
     const int node = P.node0 + blockIdx.z;
     const int N = P.N, D = P.D, bspan = P.bspan;
@@ -328,7 +379,7 @@ back_tile_kernel(const BackParams P) {
     const long long nb = (long long)blockIdx.z * P.stride;
     const bool rowok = ix < N;
     const bool vecok = (N & 3) == 0;
-    float dsum = 0.f;
+    float dsum = 0.f, dsum2 = 0.f, dsum3 = 0.f;   // HP: <p,Hp>, (unused), <Hp,Hp> ; RESID0: <r,r>
     if (MODE == BACK_PLAIN || MODE == BACK_COLNORM2) {
         if (rowok) {
 #pragma unroll
@@ -367,8 +418,10 @@ back_tile_kernel(const BackParams P) {
                     const float c = vc[px + 1];
                     const float lap = ((c - vu[px]) + (c - vd[px])) + ((c - vc[px]) + (c - vc[px + 2]));
                     const float hv = acc[4 * h + px] + fmaf(dd[px], c, P.mu * lap);
-                    if (MODE == BACK_HP) { res[px] = hv; dsum = fmaf(c, hv, dsum); }
-                    else { const float rr = rh[px] - hv; res[px] = rr; dsum = fmaf(rr, rr, dsum); }
+                    if (MODE == BACK_HP) {
+                        res[px] = hv;
+                        dsum = fmaf(c, hv, dsum); dsum3 = fmaf(hv, hv, dsum3);
+                    } else { const float rr = rh[px] - hv; res[px] = rr; dsum = fmaf(rr, rr, dsum); }
                 }
                 st4(P.out + nb + g, make_float4(res[0], res[1], res[2], res[3]));
                 if (MODE == BACK_RESID0) st4(P.p_out + nb + g, make_float4(res[0], res[1], res[2], res[3]));
@@ -401,6 +454,7 @@ back_tile_kernel(const BackParams P) {
                     if (MODE == BACK_HP) {
                         res[px] = hv;
                         dsum = fmaf(c, hv, dsum);
+                        dsum3 = fmaf(hv, hv, dsum3);
                     } else {
                         const float rr = (P.rhs0[nb + g + px] + P.tvterm[nb + g + px]) - hv;
                         res[px] = rr;
@@ -420,11 +474,18 @@ back_tile_kernel(const BackParams P) {
                 }
             }
         }
-        float vsum[1] = {dsum};
-        block_sum<1>(vsum, red);
         const int nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
-        grid_reduce_store<1>(vsum, P.part + (long long)blockIdx.z * nblk, P.counter + blockIdx.z, blk, nblk,
-                             P.scal + (long long)node * NSCAL + P.dot_slot, red);
+        if (MODE == BACK_HP) {   // S_PHP, S_RHP, S_HPHP are consecutive slots
+            float vsum[3] = {dsum, dsum2, dsum3};
+            block_sum<3>(vsum, red);
+            grid_reduce_store<3>(vsum, P.part + (long long)blockIdx.z * nblk * 3, P.counter + blockIdx.z, blk, nblk,
+                                 P.scal + (long long)node * NSCAL + P.dot_slot, red);
+        } else {
+            float vsum[1] = {dsum};
+            block_sum<1>(vsum, red);
+            grid_reduce_store<1>(vsum, P.part + (long long)blockIdx.z * nblk, P.counter + blockIdx.z, blk, nblk,
+                                 P.scal + (long long)node * NSCAL + P.dot_slot, red);
+        }
     }
 }
 
@@ -446,7 +507,7 @@ cudaError_t launch_forward(const FwdParams& P, int nodes, int max_chunks, const 
         configured_span = P.span;
     }
     dim3 grid(P.nTi * P.nSeg * max_chunks, nodes, 2);
-    { ProfScope ps(P.r ? KC_FWD_FUSED : KC_FWD, st); fwd_strip_kernel<<<grid, FTHREADS, smem, st>>>(P); }
+    { ProfScope ps(P.mode ? KC_FWD_FUSED : KC_FWD, st); fwd_strip_kernel<<<grid, FTHREADS, smem, st>>>(P); }
     dim3 rgrid(R.A1 - R.A0, (R.D + 255) / 256);
     if (rgrid.x > 0) { ProfScope ps(KC_FWD_REDUCE, st); fwd_reduce_kernel<<<rgrid, 256, 0, st>>>(R); }
     return cudaGetLastError();

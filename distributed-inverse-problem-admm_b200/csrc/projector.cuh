@@ -26,11 +26,20 @@ struct FwdParams {
     int node0;               // first node of this launch
     int N, D;
     int nTi, nSeg, span, seg;  // seg = steps per segment
-    // optional fused CG direction update p_new = r + beta * p_old (img = p_old)
-    const float* r;          // [nodes][N*N] or nullptr
+    // mode 1: fused CG direction update p_new = r + beta * p_old (img = p_old), beta = scal[beta_num]/scal[beta_den]
+    // mode 2: fully fused CG step   alpha = rr/<p,Hp>; x += alpha p; r' = r - alpha Hp; p' = r' + beta p with
+    //         beta = max(0, rr'/rr), rr' = alpha^2 <Hp,Hp> - rr (CG conjugacy); exact <r',r'> -> scal[rr_out]
+    const float* r;          // [nodes][N*N] or nullptr (mode 0)
     float* p_out;            // [nodes][N*N]
-    const double* scal;      // [V][NSCAL] node scalars
-    int beta_num, beta_den;  // scalar slots: beta = scal[beta_num] / scal[beta_den]
+    double* scal;            // [V][NSCAL] node scalars
+    int beta_num, beta_den;  // mode 1 scalar slots; mode 2: beta_den = slot of rr (in), beta_num unused
+    int mode;
+    const float* hp;         // mode 2: H p_old
+    float* x_io;             // mode 2: x (in place)
+    float* r_out;            // mode 2: r' (must not alias r)
+    float* part;             // mode 2 reduction workspace [nodes][nTi*nSeg]
+    unsigned* counter;       // [nodes]
+    int rr_out;              // mode 2: slot receiving <r', r'>
 };
 
 struct FwdReduceParams {
@@ -66,6 +75,7 @@ struct BackParams {
     int node0, N, D, bspan;
     // epilogue inputs
     const float* v;          // p (BACK_HP) or x (BACK_RESID0)
+    const float* rvec;       // (unused)
     const float* rhoD_vec;   // [nodes][N*N] or nullptr
     const float* rhoD_s;     // [V] scalar rho*D_i (used when rhoD_vec == nullptr)
     float mu;
@@ -84,11 +94,12 @@ constexpr int NSCAL = 16;  // doubles per node in the scalar table
 enum ScalSlot : int {
     S_RR0 = 0, S_RR1 = 1,   // <r,r> ping-pong by CG iteration parity
     S_PHP = 2,              // <p, Hp>
-    S_TV = 3,               // canonical TV(x)
-    S_GN2 = 4,              // |g|^2 stationarity
-    S_IMG = 5,              // |x - x_true|^2
-    S_MSE = 6,              // |Ax - b|^2
-    S_ALPHA = 7             // last alpha (diagnostic)
+    S_RHP = 3,              // (reserved: <r, Hp>, equal to <p, Hp> for CG directions)
+    S_HPHP = 4,             // <Hp, Hp>
+    S_TV = 5,               // canonical TV(x)
+    S_GN2 = 6,              // |g|^2 stationarity
+    S_IMG = 7,              // |x - x_true|^2
+    S_MSE = 8               // |Ax - b|^2
 };
 
 }  // namespace admm

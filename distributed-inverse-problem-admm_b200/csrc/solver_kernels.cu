@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_seg(const float* __restrict__ row, int c, i
 
 __global__ void __launch_bounds__(TVX * TVY)
 tv_fused_kernel(const TvParams P) {
-    __shared__ float red[96];
+    __shared__ __align__(16) float red[96];
     const int N = P.N;
     const int node = P.node0 + blockIdx.z;
     const long long nb = (long long)blockIdx.z * P.stride;
@@ -204,20 +204,21 @@ tv_fused_kernel(const TvParams P) {
 // =================================================================================================
 __global__ void __launch_bounds__(256)
 cg_update_kernel(const CgParams P) {
-    __shared__ float red[64];
+    __shared__ __align__(16) float red[64];
     const int node = P.node0 + blockIdx.y;
     const double* sc = P.scal + (long long)node * NSCAL;
     const double php = sc[S_PHP], rr = sc[P.rr_in];
     const float alpha = (php > 0.0) ? (float)(rr / php) : 0.f;
     const long long nb = (long long)blockIdx.y * P.stride;
     float* __restrict__ x = P.x + nb;
-    float* __restrict__ r = P.r + nb;
+    float* r = P.r + nb;
+    const float* rin = (P.r_in ? P.r_in : P.r) + nb;
     const float* __restrict__ p = P.p + nb;
     const float* __restrict__ hp = P.hp + nb;
     float s = 0.f;
     const long long n4 = P.n >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        float4 xv = ld4(x + 4 * i), rv = ld4(r + 4 * i);
+        float4 xv = ld4(x + 4 * i), rv = ld4(rin + 4 * i);
         const float4 pv = ld4(p + 4 * i), hv = ld4(hp + 4 * i);
         xv.x = fmaf(alpha, pv.x, xv.x); xv.y = fmaf(alpha, pv.y, xv.y);
         xv.z = fmaf(alpha, pv.z, xv.z); xv.w = fmaf(alpha, pv.w, xv.w);
@@ -228,7 +229,7 @@ cg_update_kernel(const CgParams P) {
     }
     if (blockIdx.x == 0)
         for (long long i = 4 * n4 + threadIdx.x; i < P.n; i += blockDim.x) {
-            const float xv = fmaf(alpha, p[i], x[i]), rv = fmaf(-alpha, hp[i], r[i]);
+            const float xv = fmaf(alpha, p[i], x[i]), rv = fmaf(-alpha, hp[i], rin[i]);
             x[i] = xv; r[i] = rv; s = fmaf(rv, rv, s);
         }
     float v[1] = {s};
@@ -277,7 +278,7 @@ sino_axpy_kernel(const SinoParams P) {
 // |A x - b|^2 per node -> scal[S_MSE]   (one block per node: deterministic)
 __global__ void __launch_bounds__(256)
 sino_resid_kernel(const SinoParams P) {
-    __shared__ float red[32];
+    __shared__ __align__(16) float red[32];
     __shared__ double dred[8];
     const int node = P.node0 + blockIdx.x;
     const long long beg = (long long)P.aptr[node] * P.D, end = (long long)P.aptr[node + 1] * P.D;
@@ -375,7 +376,7 @@ __device__ __forceinline__ void edge_elem(const EdgePtrs& e, float zo, float xiv
 
 __global__ void __launch_bounds__(256)
 edge_kernel(const EdgeParams P) {
-    __shared__ float red[160];
+    __shared__ __align__(16) float red[160];
     const EdgeDesc d = P.edges[blockIdx.y];
     EdgePtrs e;
     e.xi = reinterpret_cast<const float*>(d.xi); e.xj = reinterpret_cast<const float*>(d.xj);

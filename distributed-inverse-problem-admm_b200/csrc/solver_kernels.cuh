@@ -19,6 +19,7 @@ struct TvParams {
 
 struct CgParams {
     float* x; float* r; const float* p; const float* hp; float* p_out;
+    const float* r_in;     // residual to read (nullptr: r, in place)
     long long stride, n;
     int node0, rr_in, rr_out;
     float* part; unsigned* counter; double* scal;

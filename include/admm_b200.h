@@ -32,10 +32,12 @@ extern "C" {
 #define ADMM_S_RR0 0
 #define ADMM_S_RR1 1
 #define ADMM_S_PHP 2
-#define ADMM_S_TV 3
-#define ADMM_S_GN2 4
-#define ADMM_S_IMG 5
-#define ADMM_S_MSE 6
+#define ADMM_S_RHP 3
+#define ADMM_S_HPHP 4
+#define ADMM_S_TV 5
+#define ADMM_S_GN2 6
+#define ADMM_S_IMG 7
+#define ADMM_S_MSE 8
 
 typedef struct admm_plan admm_plan; /* opaque: geometry of the nodes resident on one GPU */
 
@@ -43,7 +45,8 @@ typedef struct admm_plan admm_plan; /* opaque: geometry of the nodes resident on
  * local nodes with `stride` floats between node images. */
 typedef struct admm_state {
     float* x;                 /* [V][n]  iterates x_i                      (block_6_ver2:36)            */
-    float* r;                 /* [V][n]  CG residual                                                    */
+    float* r;                 /* [V][n]  CG residual (the final residual of a solve always lands here)   */
+    float* r1;                /* [V][n]  CG residual, second buffer of the fully fused CG step (fuse 2)  */
     float* p0;                /* [V][n]  CG direction (ping)                                            */
     float* p1;                /* [V][n]  CG direction (pong)                                            */
     float* hp;                /* [V][n]  H p                                                            */
@@ -65,7 +68,8 @@ typedef struct admm_state {
     long long stride;         /* floats between node images (>= n)                                      */
     float rho, lam, mu, q_uniform;
     int w_parity;             /* 0: w0 current, 1: w1 current (caller flips it by sweeps&1 after x-updates) */
-    int fuse_pupdate;         /* 1: fuse p = r + beta p into the forward projector                      */
+    int fuse_pupdate;         /* 0: separate kernels; 1: p = r + beta p fused into the forward projector;
+                                 2: the whole CG vector update (x, r, p) fused into the forward projector  */
     int defer_tv;             /* 1: admm_x_update skips the LAST sweep's TV pass; the caller runs admm_tv_pass
                                  itself (lets the cut-edge exchange start before the TV kernel)         */
     int reuse_ax;             /* 1: admm_x_update takes A x from `ax` (kept current by the CG recurrence) instead of

@@ -56,7 +56,7 @@ def test_ring_uniform_q_200_iterations():
     assert np.stack(xg).shape == (V, N * N)
 
 
-@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("fuse", [True, 1, False])
 def test_regular_graph_w_precisions_weighted(fuse):
     """block_3 arithmetic-mean Q from column norms, heterogeneous node precisions, W-weighted z (PDF eq. 2),
     reference_literal angle sets (both projector orientations in every node), 2 TV sweeps."""

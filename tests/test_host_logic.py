@@ -121,7 +121,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert not missing, missing
     assert set(nat.EXPORTS) <= declared
     assert L.admm_version() == 100
-    assert ctypes.sizeof(nat.State) == 20 * 8 + 8 + 4 * 4 + 4 * 4
+    assert ctypes.sizeof(nat.State) == 21 * 8 + 8 + 4 * 4 + 4 * 4
 
 
 def test_no_cpu_fallback_without_device():
