@@ -377,7 +377,7 @@ def main():
     nz = 1 if eng.rhoD_vec is not None else 0
     deg_sum = sum(G.degree(g) for g in eng.loc)
     alg = {  # algorithmic bytes per launch (this rank), DESIGN.md "Kernels"
-        "fwd": 4 * (Vl * n + m_loc), "fwd_fused": 4 * (3 * Vl * n + m_loc),
+        "fwd": 4 * (Vl * n + m_loc), "fwd_fused": 4 * ((7 if not args.no_fuse else 3) * Vl * n + m_loc),
         "back_hp": 4 * (m_loc + (2 + nz) * Vl * n), "back_resid0": 4 * (m_loc + (5 + nz) * Vl * n),
         "cg_update": 4 * 6 * Vl * n, "p_update": 4 * 3 * Vl * n, "tv": 4 * 9 * Vl * n,
         "rhs0": 4 * ((2 + nz) * deg_sum + 2 * Vl) * n, "edge": 4 * 8 * n * max(El, 1),

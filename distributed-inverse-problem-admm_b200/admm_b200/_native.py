@@ -91,7 +91,7 @@ def lib():
     L.admm_tv_pass.argtypes = [vp, ctypes.POINTER(State), i, i, i, vp]
     L.admm_edge_update.argtypes = [vp, ctypes.POINTER(State), vp, i, vp, vp]
     L.admm_pack.argtypes = [vp, vp, i, vp]
-    L.admm_finalize.argtypes = [vp, ctypes.POINTER(State), vp, vp, vp, vp, i, vp, i, vp, vp]
+    L.admm_finalize.argtypes = [vp, ctypes.POINTER(State), vp, vp, vp, vp, i, i, vp, vp, vp, vp, i, vp, vp]
     L.admm_grad2d_host.argtypes = [i, vp, vp, vp]
     L.admm_div2d_host.argtypes = [i, vp, vp, i, vp]
     L.admm_kt_subgrad_host.argtypes = [i, vp, d, i, vp, vp]

@@ -219,6 +219,14 @@ class ADMMEngine:
         self.edge_desc = torch.tensor(ed if ed else [[0] * 11], dtype=torch.int64, device=self.dev)
         i32 = lambda a: torch.tensor(a if len(a) else [0], dtype=torch.int32, device=self.dev)  # noqa: E731
         self.edge_gi, self.edge_gj, self.edge_fl = i32(gi), i32(gj), i32(fl)
+        epos_of = {le.e: k for k, le in enumerate(ordered)}       # global edge id -> position in the edge arrays
+        fptr, fepos, fend = [0], [], []
+        for g in self.loc:
+            for kk in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1]):
+                fepos.append(epos_of[int(sp.nbr_edge[kk])])
+                fend.append(int(sp.nbr_end[kk]))
+            fptr.append(len(fepos))
+        self.fin_ptr, self.fin_epos, self.fin_end = i32(fptr), i32(fepos), i32(fend)
         self.node_gid = i32(self.loc)
         self.pack_desc = torch.tensor(packs if packs else [[0, 0, 0]], dtype=torch.int64, device=self.dev)
         self.n_pack = len(packs)
@@ -284,7 +292,8 @@ class ADMMEngine:
             nat.check(L.admm_edge_update(h, sref, self.edge_desc.data_ptr() + nl * esz, E - nl,
                                          self.sums.data_ptr() + nl * 5 * 8, self._stream()), "admm_edge_update")
         nat.check(L.admm_finalize(h, sref, self.sums.data_ptr(), self.edge_gi.data_ptr(), self.edge_gj.data_ptr(),
-                                  self.edge_fl.data_ptr(), self.E, self.node_gid.data_ptr(), self.Vg,
+                                  self.edge_fl.data_ptr(), self.E, self.n_edges_local, self.node_gid.data_ptr(),
+                                  self.fin_ptr.data_ptr(), self.fin_epos.data_ptr(), self.fin_end.data_ptr(), self.Vg,
                                   self.row.data_ptr(), self._stream()), "admm_finalize")
         if self.world > 1:
             self.dist.all_reduce(self.row, group=self.group)  # the only collective

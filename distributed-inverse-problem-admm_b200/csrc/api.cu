@@ -481,12 +481,14 @@ extern "C" int admm_pack(admm_plan* p, const admm_pack_item* d_items, int nitems
 }
 
 extern "C" int admm_finalize(admm_plan* p, const admm_state* s, const double* d_sums, const int* d_edge_gi,
-                             const int* d_edge_gj, const int* d_edge_flags, int nedges, const int* d_node_gid, int Vg,
-                             double* d_row, void* stream) {
-    if (!p || !s || !d_row || !d_node_gid) return fail(ADMM_ERR_ARG, "admm_finalize: null argument");
+                             const int* d_edge_gj, const int* d_edge_flags, int nedges, int nedges_local,
+                             const int* d_node_gid, const int* d_nbr_ptr, const int* d_nbr_epos, const int* d_nbr_end,
+                             int Vg, double* d_row, void* stream) {
+    if (!p || !s || !d_row || !d_node_gid || !d_nbr_ptr) return fail(ADMM_ERR_ARG, "admm_finalize: null argument");
     FinalizeParams F{};
     F.sums = d_sums; F.edge_gi = d_edge_gi; F.edge_gj = d_edge_gj; F.edge_flags = d_edge_flags; F.scal = s->scal;
-    F.node_gid = d_node_gid; F.row = d_row; F.E = nedges; F.V = p->V; F.Vg = Vg; F.rho = s->rho;
+    F.node_gid = d_node_gid; F.row = d_row; F.E = nedges; F.E_local = nedges_local; F.V = p->V; F.Vg = Vg; F.rho = s->rho;
+    F.nbr_ptr = d_nbr_ptr; F.nbr_epos = d_nbr_epos; F.nbr_end = d_nbr_end;
     CK(launch_finalize(F, (cudaStream_t)stream));
     return ADMM_OK;
 }

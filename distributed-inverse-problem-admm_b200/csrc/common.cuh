@@ -135,6 +135,8 @@ __device__ __forceinline__ void lds_pair(unsigned addr, float& a, float& b) {
 __device__ __forceinline__ void opaque(unsigned& v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ void opaque(float& v) { asm volatile("" : "+f"(v)); }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 

@@ -190,6 +190,31 @@ fwd_strip_kernel(const FwdParams P) {
             S[k * FPITCH + FW + 4] = 0.f;
         }
         __syncthreads();
+        // ---- pull the next slab's operands towards L2 while this slab is sampled (staging is latency-bound) ----
+        if (slab + 1 < nslab) {
+            const int K1 = K0 + FL;
+            if (xdom) {
+                for (int idx = tid; idx < FW * (FL / 32); idx += FTHREADS) {   // one 128-byte line per request
+                    const int u = idx / (FL / 32), kk = (idx % (FL / 32)) * 32;
+                    if (u < Wt && K1 + kk < N) {
+                        const long long g = (long long)(U0 + u) * N + K1 + kk;
+                        prefetch_l2(img + g);
+                        if (mode != 0) prefetch_l2(rimg + g);
+                        if (mode == 2) { prefetch_l2(hpimg + g); if (writer) prefetch_l2(xio + g); }
+                    }
+                }
+            } else {
+                for (int idx = tid; idx < FL * ((FW + 31) / 32); idx += FTHREADS) {
+                    const int k = idx / ((FW + 31) / 32), uu = (idx % ((FW + 31) / 32)) * 32;
+                    if (K1 + k < N && uu < Wt) {
+                        const long long g = (long long)(K1 + k) * N + U0 + uu;
+                        prefetch_l2(img + g);
+                        if (mode != 0) prefetch_l2(rimg + g);
+                        if (mode == 2) { prefetch_l2(hpimg + g); if (writer) prefetch_l2(xio + g); }
+                    }
+                }
+            }
+        }
         // ---- sample ---------------------------------------------------------------------------------
         for (int ai = slot; ai < na; ai += FTHREADS / FTPA) {
             const int4 win = s_win[ai];

@@ -441,33 +441,55 @@ pack_kernel(const PackParams P) {
 // order, fp64, like the reference's Python floats) and the per-node scalars into one history row
 //   row = [r2, s2, pri_node[Vg], dual_node[Vg], pen[Vg], mse[Vg], tv[Vg], gn2[Vg], img[Vg]]
 // Rows of different ranks are summed by the caller (ncclAllReduce) when nodes are sharded.
-__global__ void finalize_kernel(const FinalizeParams P) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int Vg = P.Vg;
+__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams P) {
+    __shared__ double red2[2][8];
+    const int Vg = P.Vg, tid = threadIdx.x;
     double* row = P.row;
-    for (int i = 0; i < 2 + 7 * Vg; ++i) row[i] = 0.0;
     double* pri = row + 2; double* dual = pri + Vg; double* pen = dual + Vg;
     double* mse = pen + Vg; double* tv = mse + Vg; double* gn2 = tv + Vg; double* img = gn2 + Vg;
     const double rho2 = (double)P.rho * (double)P.rho;
-    double r2 = 0.0, s2 = 0.0;
-    for (int e = 0; e < P.E; ++e) {
-        const double* s = P.sums + (long long)e * 5;
-        const int gi = P.edge_gi[e], gj = P.edge_gj[e], fl = P.edge_flags[e];
-        double acc = 0.0;
-        if (fl & 1) { acc += s[0]; pri[gi] += s[0]; pen[gi] += s[3]; }
-        if (fl & 2) { acc += s[1]; pri[gj] += s[1]; pen[gj] += s[4]; }
-        r2 += acc;
-        if (fl & 4) {  // this rank owns the edge's dual residual
-            s2 += rho2 * s[2];
-            dual[gi] += rho2 * s[2];
-            dual[gj] += rho2 * s[2];
-        }
-    }
-    row[0] = r2; row[1] = s2;
-    for (int v = 0; v < P.V; ++v) {
-        const double* sc = P.scal + (long long)v * NSCAL;
+    for (int i = tid; i < 2 + 7 * Vg; i += blockDim.x) row[i] = 0.0;
+    __syncthreads();
+    // per local node, over its incident edges in G.neighbors() order
+    for (int v = tid; v < P.V; v += blockDim.x) {
         const int g = P.node_gid[v];
+        double a = 0.0, b = 0.0, d = 0.0;
+        for (int k = P.nbr_ptr[v]; k < P.nbr_ptr[v + 1]; ++k) {
+            const int e = P.nbr_epos[k], end = P.nbr_end[k];
+            const double* s = P.sums + (long long)e * 5;
+            a += s[end];
+            b += s[3 + end];
+            if (P.edge_flags[e] & 4) d += rho2 * s[2];
+        }
+        const double* sc = P.scal + (long long)v * NSCAL;
+        pri[g] = a; pen[g] = b; dual[g] = d;
         mse[g] = sc[S_MSE]; tv[g] = sc[S_TV]; gn2[g] = sc[S_GN2]; img[g] = sc[S_IMG];
+    }
+    // totals: fixed-order strided partials + fixed tree
+    double r2 = 0.0, s2 = 0.0;
+    for (int e = tid; e < P.E; e += blockDim.x) {
+        const double* s = P.sums + (long long)e * 5;
+        const int fl = P.edge_flags[e];
+        if (fl & 1) r2 += s[0];
+        if (fl & 2) r2 += s[1];
+        if (fl & 4) s2 += rho2 * s[2];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((tid & 31) == 0) { red2[0][tid >> 5] = r2; red2[1][tid >> 5] = s2; }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red2[0][w]; b += red2[1][w]; }
+        row[0] = a; row[1] = b;
+        // dual residual of owned cut edges also belongs to the REMOTE end's node (block_6_ver2:251-253)
+        for (int e = P.E_local; e < P.E; ++e) {
+            const int fl = P.edge_flags[e];
+            if ((fl & 4) && !(fl & 2)) dual[P.edge_gj[e]] += rho2 * P.sums[(long long)e * 5 + 2];
+        }
     }
 }
 
@@ -516,7 +538,7 @@ cudaError_t launch_pack(const PackParams& P, int nitems, cudaStream_t st) {
     return cudaGetLastError();
 }
 cudaError_t launch_finalize(const FinalizeParams& P, cudaStream_t st) {
-    { ProfScope ps(KC_FINALIZE, st); finalize_kernel<<<1, 32, 0, st>>>(P); }
+    { ProfScope ps(KC_FINALIZE, st); finalize_kernel<<<1, 256, 0, st>>>(P); }
     return cudaGetLastError();
 }
 

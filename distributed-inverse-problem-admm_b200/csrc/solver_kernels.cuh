@@ -70,8 +70,11 @@ struct FinalizeParams {
     const int* edge_flags;    // bit0: i local, bit1: j local, bit2: owns the dual residual
     const double* scal;       // [V][NSCAL]
     const int* node_gid;      // [V]
+    const int* nbr_ptr;       // [V+1] incident-edge lists of the local nodes (G.neighbors order)
+    const int* nbr_epos;      // [nnz] position of the edge in the sums / flags arrays
+    const int* nbr_end;       // [nnz] 0: the node is the edge's min end, 1: max end
     double* row;              // [2 + 7*Vg]
-    int E, V, Vg;
+    int E, E_local, V, Vg;    // edges [E_local, E) are the cut edges
     float rho;
 };
 

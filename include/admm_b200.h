@@ -140,10 +140,14 @@ int admm_x_update(admm_plan* plan, admm_state* st, int node0, int nodes, int swe
 int admm_edge_update(admm_plan* plan, const admm_state* st, const admm_edge* d_edges, int nedges,
                      double* d_sums, void* stream);
 int admm_pack(admm_plan* plan, const admm_pack_item* d_items, int nitems, void* stream);
-/* history row [r2, s2, pri_node[Vg], dual_node[Vg], pen[Vg], mse[Vg], tv[Vg], gn2[Vg], img[Vg]] (doubles) */
+/* history row [r2, s2, pri_node[Vg], dual_node[Vg], pen[Vg], mse[Vg], tv[Vg], gn2[Vg], img[Vg]] (doubles).
+ * Edge arrays list the rank's local edges first (nedges_local), then its cut edges; flags: bit0 i local, bit1 j
+ * local, bit2 this rank owns the edge's dual residual.  nbr_* = incident-edge CSR of the local nodes
+ * (G.neighbors order): position of the edge in the edge arrays and which end the node is. */
 int admm_finalize(admm_plan* plan, const admm_state* st, const double* d_sums, const int* d_edge_gi,
-                  const int* d_edge_gj, const int* d_edge_flags, int nedges, const int* d_node_gid, int Vg,
-                  double* d_row, void* stream);
+                  const int* d_edge_gj, const int* d_edge_flags, int nedges, int nedges_local,
+                  const int* d_node_gid, const int* d_nbr_ptr, const int* d_nbr_epos, const int* d_nbr_end,
+                  int Vg, double* d_row, void* stream);
 
 /* ---- block_4 helpers on device (block_4_tv_helpers.py:17-46): one TV pass without a CG solve ------------
  * used by the drop-in block_4 module; outputs w', tvterm' and TV(x) like the fused K3. */
