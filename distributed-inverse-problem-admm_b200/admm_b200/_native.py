@@ -95,9 +95,13 @@ def lib():
     L.admm_grad2d_host.argtypes = [i, vp, vp, vp]
     L.admm_div2d_host.argtypes = [i, vp, vp, i, vp]
     L.admm_kt_subgrad_host.argtypes = [i, vp, d, i, vp, vp]
+    L.admm_ipc_alloc.argtypes = [ll, ctypes.POINTER(vp), vp]
+    L.admm_ipc_open.argtypes = [vp, ctypes.POINTER(vp)]
+    L.admm_ipc_close.argtypes = [vp]
+    L.admm_ipc_free.argtypes = [vp]
     L.admm_profile_enable.argtypes = [i]
     L.admm_profile_read.argtypes = [vp, vp]
-    for name in ("admm_grad2d_host", "admm_div2d_host", "admm_kt_subgrad_host", "admm_profile_enable", "admm_profile_read", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host", "admm_adjoint_host",
+    for name in ("admm_ipc_alloc", "admm_ipc_open", "admm_ipc_close", "admm_ipc_free", "admm_grad2d_host", "admm_div2d_host", "admm_kt_subgrad_host", "admm_profile_enable", "admm_profile_read", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host", "admm_adjoint_host",
                  "admm_rhs0", "admm_x_update", "admm_tv_pass", "admm_edge_update", "admm_pack", "admm_finalize"):
         getattr(L, name).restype = i
     _lib = L
@@ -108,7 +112,7 @@ EXPORTS = ("admm_version", "admm_last_error", "admm_device_count", "admm_plan_cr
            "admm_plan_info", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host",
            "admm_adjoint_host", "admm_colnorm2_host", "admm_rhs0", "admm_x_update", "admm_edge_update", "admm_pack", "admm_finalize",
            "admm_tv_pass", "admm_launch_count", "admm_profile_enable", "admm_profile_read", "admm_grad2d_host",
-           "admm_div2d_host", "admm_kt_subgrad_host")
+           "admm_div2d_host", "admm_kt_subgrad_host", "admm_ipc_alloc", "admm_ipc_open", "admm_ipc_close", "admm_ipc_free")
 
 KC_NAMES = ("fwd", "fwd_reduce", "back_plain", "back_hp", "back_resid0", "colnorm2", "tv", "cg_update", "p_update",
             "sino_axpy", "sino_resid", "rhs0", "edge", "pack", "finalize", "fwd_fused")

@@ -39,7 +39,7 @@ class ADMMEngine:
     def __init__(self, thetas, sinograms, G, N, D=None, det_w=2.0, lam_tv=0.01, rho=1.0, Q=None, Wi_list=None,
                  node_prec=None, tv_mu=None, tv_sweeps=1, cg_iters=8, phantom_true=None, weighted_z=False,
                  device=0, dist=None, rank=0, world=1, group=None, node_group=None, fuse_pupdate=True,
-                 max_iters=200, ax_refresh_every=10):
+                 max_iters=200, ax_refresh_every=10, exchange="auto"):
         torch = _torch()
         nat.require_cuda()
         self.torch = torch
@@ -51,6 +51,7 @@ class ADMMEngine:
         self.mu = float(tv_mu if tv_mu is not None else rho)
         self.S, self.C = int(tv_sweeps), int(cg_iters)
         self.dist, self.rank, self.world, self.group = dist, int(rank), int(world), group
+        self._G = G
         self.sp: ShardPlan = build_shard_plan(G, self.world, self.rank)
         sp = self.sp
         self.Vg = sp.V
@@ -136,9 +137,12 @@ class ADMMEngine:
             self.Wmap = {g: k for k, g in enumerate(need)}
             self.W = torch.from_numpy(np.stack([np.asarray(Wi_list[g], dtype=np.float32).reshape(-1) for g in need])).to(self.dev)
 
-        # exchange buffers (cut edges), one contiguous block per peer
-        self.send = {p: z(len(sp.exch[p]), n) for p in sp.peers}
-        self.recv = {p: z(len(sp.exch[p]), n) for p in sp.peers}
+        # ---- cut-edge exchange: peer memory over NVLink (CUDA IPC) when available, NCCL send/recv otherwise -------
+        self.exchange_mode = "none" if self.world == 1 else self._setup_peer_memory(exchange)
+        self.send, self.recv = {}, {}
+        if self.exchange_mode == "nccl":   # one contiguous block per peer
+            self.send = {p: z(len(sp.exch[p]), n) for p in sp.peers}
+            self.recv = {p: z(len(sp.exch[p]), n) for p in sp.peers}
 
         # the (pinned) host landing buffer of the final x download is page-locked in the background while the
         # GPU iterates (cudaHostAlloc of GBs takes longer than the copy itself)
@@ -168,6 +172,66 @@ class ADMMEngine:
         for i, s in zip(idx, t.stride()):
             off += i * s
         return t.data_ptr() + off * t.element_size()
+
+    def _setup_peer_memory(self, exchange):
+        """Allocate this rank's double-buffered send buffer through the C ABI (cudaMalloc + IPC handle), ship the
+        handle to the peers and map theirs.  Returns "p2p" on success on every rank, else "nccl"."""
+        import ctypes as C
+        L, sp, dist = nat.lib(), self.sp, self.dist
+        cut_sorted = sorted(le.e for le in sp.local_edges if le.peer >= 0)
+        self._my_slot = {e: k for k, e in enumerate(cut_sorted)}
+        self._ncut = len(cut_sorted)
+        self._peer_base, self._peer_slot, self._peer_ncut = {}, {}, {}
+        self._ipc_mine, self._ipc_opened = None, []
+        if exchange == "nccl":
+            return "nccl"
+        ok, handle = 1, b""
+        try:
+            ptr = C.c_void_p()
+            buf = (C.c_ubyte * 64)()
+            nbytes = 2 * max(self._ncut, 1) * self.n * 4
+            nat.check(L.admm_ipc_alloc(nbytes, C.byref(ptr), buf), "admm_ipc_alloc")
+            self._ipc_mine = ptr.value
+            handle = bytes(buf)
+        except Exception:
+            ok = 0
+        infos = [None] * self.world
+        dist.all_gather_object(infos, (ok, handle, self._ncut), group=self.group)
+        if all(i[0] for i in infos):
+            try:
+                for p in sp.peers:
+                    ptr = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(infos[p][1])
+                    nat.check(L.admm_ipc_open(hb, C.byref(ptr)), "admm_ipc_open")
+                    self._peer_base[p] = ptr.value
+                    self._ipc_opened.append(ptr.value)
+                    self._peer_ncut[p] = infos[p][2]
+                    sp_p = build_shard_plan(self._G, self.world, p)
+                    self._peer_slot[p] = {e: k for k, e in enumerate(sorted(le.e for le in sp_p.local_edges if le.peer >= 0))}
+            except Exception:
+                ok = 0
+        else:
+            ok = 0
+        flag = self.torch.tensor([ok], dtype=self.torch.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            self._bar = self.torch.zeros(1, dtype=self.torch.float32, device=self.dev)
+            return "p2p"
+        if exchange == "p2p":
+            raise RuntimeError("peer-memory exchange requested but CUDA IPC setup failed on some rank")
+        return "nccl"
+
+    def _remote_a(self, le, parity):
+        """Device address (on THIS GPU's address space) of the remote end's a = x + y of cut edge `le`."""
+        if self.exchange_mode == "p2p":
+            p = le.peer
+            return self._peer_base[p] + (parity * max(self._peer_ncut[p], 1) + self._peer_slot[p][le.e]) * self.n * 4
+        return self._addr(self.recv[le.peer], le.xslot)
+
+    def _pack_out(self, le, parity):
+        if self.exchange_mode == "p2p":
+            return self._ipc_mine + (parity * max(self._ncut, 1) + self._my_slot[le.e]) * self.n * 4
+        return self._addr(self.send[le.peer], le.xslot)
 
     def _build_tables(self):
         torch, sp = self.torch, self.sp
@@ -201,8 +265,8 @@ class ADMMEngine:
             xj = self._addr(self.x, sp.g2l[le.gj]) if le.j_local else 0
             yi = self._addr(self.y, s, 0) if le.i_local else 0
             yj = self._addr(self.y, s, 1) if le.j_local else 0
-            ai = self._addr(self.recv[le.peer], le.xslot) if not le.i_local else 0
-            aj = self._addr(self.recv[le.peer], le.xslot) if not le.j_local else 0
+            ai = self._remote_a(le, 0) if not le.i_local else 0
+            aj = self._remote_a(le, 0) if not le.j_local else 0
             Wi = self._addr(self.W, self.Wmap[le.gi]) if self.W is not None else 0
             Wj = self._addr(self.W, self.Wmap[le.gj]) if self.W is not None else 0
             qij = self._addr(self.Qdir, self.dirslot[(le.gi, le.gj)]) if (self.Qdir is not None and le.i_local) else 0
@@ -212,10 +276,7 @@ class ADMMEngine:
             gj.append(le.gj)
             fl.append((1 if le.i_local else 0) | (2 if le.j_local else 0) | (4 if le.owns_dual else 0))
             if le.peer >= 0:
-                if le.i_local:
-                    packs.append([xi, yi, self._addr(self.send[le.peer], le.xslot)])
-                else:
-                    packs.append([xj, yj, self._addr(self.send[le.peer], le.xslot)])
+                packs.append([xi, yi, self._pack_out(le, 0)] if le.i_local else [xj, yj, self._pack_out(le, 0)])
         self.edge_desc = torch.tensor(ed if ed else [[0] * 11], dtype=torch.int64, device=self.dev)
         i32 = lambda a: torch.tensor(a if len(a) else [0], dtype=torch.int32, device=self.dev)  # noqa: E731
         self.edge_gi, self.edge_gj, self.edge_fl = i32(gi), i32(gj), i32(fl)
@@ -230,6 +291,20 @@ class ADMMEngine:
         self.node_gid = i32(self.loc)
         self.pack_desc = torch.tensor(packs if packs else [[0, 0, 0]], dtype=torch.int64, device=self.dev)
         self.n_pack = len(packs)
+        self.edge_desc_par = [self.edge_desc, self.edge_desc]
+        self.pack_desc_par = [self.pack_desc, self.pack_desc]
+        if self.exchange_mode == "p2p":   # second parity of the double-buffered peer-memory exchange
+            ed1 = self.edge_desc.clone()
+            pk1 = self.pack_desc.clone()
+            k = 0
+            for pos, le in enumerate(ordered):
+                if le.peer >= 0:
+                    col = 5 if not le.i_local else 6           # admm_edge.ai / .aj
+                    ed1[pos, col] = self._remote_a(le, 1)
+                    pk1[k, 2] = self._pack_out(le, 1)
+                    k += 1
+            self.edge_desc_par = [self.edge_desc, ed1]
+            self.pack_desc_par = [self.pack_desc, pk1]
 
     def _fill_state(self, fuse):
         st = self.st
@@ -270,11 +345,15 @@ class ADMMEngine:
         st.w_parity ^= 1
 
     def exchange_start(self):
-        """Pack a = x + y of this rank's cut-edge ends and post the grouped NCCL send/recv (returns the requests)."""
+        """Pack a = x + y of this rank's cut-edge ends.  NCCL mode: post the grouped send/recv and return the requests.
+        Peer-memory mode: the pack kernel writes straight into the IPC-shared buffer the peers read from."""
         if not self.n_pack:
             return []
-        nat.check(nat.lib().admm_pack(self.plan.handle, self.pack_desc.data_ptr(), self.n_pack, self._stream()),
+        par = self.k & 1 if self.exchange_mode == "p2p" else 0
+        nat.check(nat.lib().admm_pack(self.plan.handle, self.pack_desc_par[par].data_ptr(), self.n_pack, self._stream()),
                   "admm_pack")
+        if self.exchange_mode == "p2p":
+            return []
         return post_exchange(self.dist, self.sp, self.send, self.recv, self.group)
 
     def edges_phase(self, reqs=()):
@@ -283,20 +362,26 @@ class ADMMEngine:
         sref = ctypes.byref(self.st)
         nl, E = self.n_edges_local, self.E
         esz = 11 * 8
+        par = self.k & 1 if self.exchange_mode == "p2p" else 0
+        desc = self.edge_desc_par[par]
         if nl:
-            nat.check(L.admm_edge_update(h, sref, self.edge_desc.data_ptr(), nl, self.sums.data_ptr(), self._stream()),
+            nat.check(L.admm_edge_update(h, sref, desc.data_ptr(), nl, self.sums.data_ptr(), self._stream()),
                       "admm_edge_update")
+        if self.exchange_mode == "p2p":
+            # device-side barrier: every rank's pack of this iteration has completed before anyone reads it; the
+            # double buffer makes this the only synchronisation the exchange needs
+            self.dist.all_reduce(self._bar, group=self.group)
         for r in reqs:
             r.wait()          # stream-level wait: the compute stream now depends on the received buffers
         if E - nl:
-            nat.check(L.admm_edge_update(h, sref, self.edge_desc.data_ptr() + nl * esz, E - nl,
+            nat.check(L.admm_edge_update(h, sref, desc.data_ptr() + nl * esz, E - nl,
                                          self.sums.data_ptr() + nl * 5 * 8, self._stream()), "admm_edge_update")
         nat.check(L.admm_finalize(h, sref, self.sums.data_ptr(), self.edge_gi.data_ptr(), self.edge_gj.data_ptr(),
                                   self.edge_fl.data_ptr(), self.E, self.n_edges_local, self.node_gid.data_ptr(),
                                   self.fin_ptr.data_ptr(), self.fin_epos.data_ptr(), self.fin_end.data_ptr(), self.Vg,
                                   self.row.data_ptr(), self._stream()), "admm_finalize")
         if self.world > 1:
-            self.dist.all_reduce(self.row, group=self.group)  # the only collective
+            self.dist.all_reduce(self.row, group=self.group)  # the only data collective
         if self.k < self.max_iters:
             self.hist[self.k].copy_(self.row)
 
@@ -384,6 +469,17 @@ class ADMMEngine:
         return out
 
     def close(self):
+        L = nat.lib()
+        if self.world > 1 and getattr(self, "exchange_mode", "") == "p2p":
+            self.torch.cuda.synchronize(self.dev)
+            self.dist.barrier(group=self.group)      # nobody unmaps while a peer may still read
+            for ptr in self._ipc_opened:
+                L.admm_ipc_close(ctypes.c_void_p(ptr))
+            self._ipc_opened = []
+            self.dist.barrier(group=self.group)
+            if self._ipc_mine:
+                L.admm_ipc_free(ctypes.c_void_p(self._ipc_mine))
+                self._ipc_mine = None
         self.plan.close()
 
 

@@ -48,7 +48,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                        # --- B200 solver controls (not in the reference) ---
                        cg_iters=8, tv_sweeps=1, tv_mu=None, node_prec=None, weighted_z=False, scs_eps=None,
                        check_every=1, node_group=None, fuse_pupdate=True, device=None, return_engine=False,
-                       distributed=None, ax_refresh_every=10,
+                       distributed=None, ax_refresh_every=10, exchange="auto",
                        **kwargs):
     """Returns x_per_node as list of reconstructions, each length n, and the history of residual norms
     (block_6_admm_loop_ver2.py:21-24).
@@ -57,7 +57,9 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
     `tv_sweeps`, `tv_mu` select the inner work, which is fixed per outer iteration (no host round trips).
     `Qij_diag_fn` may be a callable (i, j) -> n-vector (block_3 provider), a scalar, or None (uniform 1).
     Under torch.distributed (NCCL) the nodes are sharded over the ranks; every rank returns the full result
-    (`distributed=False` keeps the whole graph on this rank's GPU).
+    (`distributed=False` keeps the whole graph on this rank's GPU).  `exchange`: "p2p" reads the cut-edge iterates
+    straight from the peers' memory over NVLink inside the edge kernel (CUDA IPC), "nccl" uses grouped send/recv,
+    "auto" picks p2p when IPC mapping works on every rank.
     """
     for k in list(kwargs):
         if k in _IGNORED:
@@ -94,7 +96,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                      cg_iters=min(int(cg_iters), int(max_inner_iters)), phantom_true=phantom_true,
                      weighted_z=weighted_z, device=device, dist=dist if world > 1 else None, rank=rank, world=world,
                      group=group, node_group=node_group, fuse_pupdate=fuse_pupdate, max_iters=max_iters,
-                     ax_refresh_every=ax_refresh_every)
+                     ax_refresh_every=ax_refresh_every, exchange=exchange)
     eng._node_prec_all = node_prec
 
     print(f"Max ADMM Iteration in Block-6 B4 Loop = {max_iters}") if verbose else None

@@ -492,3 +492,39 @@ extern "C" int admm_finalize(admm_plan* p, const admm_state* s, const double* d_
     CK(launch_finalize(F, (cudaStream_t)stream));
     return ADMM_OK;
 }
+
+// ---- peer-memory exchange buffers (CUDA IPC over NVLink) -------------------------------------------------------
+// The cut-edge iterates a = x + y are packed into a buffer that the owning rank allocates here and every peer maps
+// with cudaIpcOpenMemHandle; the peers' edge kernels then read the remote a directly over NVLink (no staging copy,
+// no send/recv kernels): the transfer overlaps the edge kernel's own HBM work.
+extern "C" int admm_ipc_alloc(long long bytes, void** d_ptr, unsigned char* handle64) {
+    if (bytes <= 0 || !d_ptr || !handle64) return fail(ADMM_ERR_ARG, "admm_ipc_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    CK(cudaMalloc(&p, (size_t)bytes));
+    CK(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(ADMM_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, 64);
+    *d_ptr = p;
+    return ADMM_OK;
+}
+extern "C" int admm_ipc_open(const unsigned char* handle64, void** d_ptr) {
+    if (!handle64 || !d_ptr) return fail(ADMM_ERR_ARG, "admm_ipc_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return ADMM_OK;
+}
+extern "C" int admm_ipc_close(void* d_ptr) {
+    if (d_ptr) CK(cudaIpcCloseMemHandle(d_ptr));
+    return ADMM_OK;
+}
+extern "C" int admm_ipc_free(void* d_ptr) {
+    if (d_ptr) CK(cudaFree(d_ptr));
+    return ADMM_OK;
+}

@@ -153,6 +153,15 @@ int admm_finalize(admm_plan* plan, const admm_state* st, const double* d_sums, c
  * used by the drop-in block_4 module; outputs w', tvterm' and TV(x) like the fused K3. */
 int admm_tv_pass(admm_plan* plan, admm_state* st, int node0, int nodes, int with_diag, void* stream);
 
+/* ---- peer-memory exchange buffers (CUDA IPC; one process per GPU) -----------------------------------------------
+ * admm_ipc_alloc: cudaMalloc + zero + cudaIpcGetMemHandle (64-byte handle, to be shipped to the peers);
+ * admm_ipc_open : map a peer's buffer on the current device (lazy peer access over NVLink).  The mapped address
+ * goes into admm_edge.ai / .aj so admm_edge_update reads the remote a = x + y in place. */
+int admm_ipc_alloc(long long bytes, void** d_ptr, unsigned char* handle64);
+int admm_ipc_open(const unsigned char* handle64, void** d_ptr);
+int admm_ipc_close(void* d_ptr);
+int admm_ipc_free(void* d_ptr);
+
 /* ---- block_4 NumPy helpers on device, HOST fp64 buffers (bit-identical to the reference's float64 NumPy) ----
  * admm_grad2d_host     : _grad_forward_2d_from_vec        block_4_tv_helpers.py:17-23
  * admm_div2d_host      : _div_backward_2d_to_vec          block_4_tv_helpers.py:25-35 (exact_adjoint=0: as shipped,

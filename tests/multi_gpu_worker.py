@@ -35,8 +35,10 @@ def main():
             Q = lambda i, j: 0.5 * (Wl[i] + Wl[j])  # noqa: E731
         kw = dict(lam_tv=0.02, rho=2.0, max_iters=25, eps_pri=0.0, eps_dual=0.0, verbose=False, phantom_true=img,
                   cg_iters=6, weighted_z=wq)
-        xs, hs = decentralized_admm(ops, sinos, G, Wl, Q, N, **kw)
+        xs, hs = decentralized_admm(ops, sinos, G, Wl, Q, N, exchange="p2p", **kw)       # peer memory over NVLink
+        xn, hn = decentralized_admm(ops, sinos, G, Wl, Q, N, exchange="nccl", **kw)      # grouped send/recv
         x1, h1 = decentralized_admm(ops, sinos, G, Wl, Q, N, distributed=False, **kw)
+        assert all(np.array_equal(a, b) for a, b in zip(xs, xn)) and hs["primal"] == hn["primal"]
         cut = cut_statistics(G, world)["cut"]
         same_x = all(np.array_equal(a, b) for a, b in zip(xs, x1))
         tr = max(np.max(np.abs(np.array(hs[k]) - np.array(h1[k])) / np.maximum(np.abs(np.array(h1[k])), 1e-30))
