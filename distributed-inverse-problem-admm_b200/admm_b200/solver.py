@@ -183,7 +183,9 @@ class ADMMEngine:
         self._ncut = len(cut_sorted)
         self._peer_base, self._peer_slot, self._peer_ncut = {}, {}, {}
         self._ipc_mine, self._ipc_opened = None, []
-        if exchange == "nccl":
+        if exchange == "nccl" or (exchange == "auto" and self.world > 2):
+            # measured on 8 B200s (profiles/README.md): pairwise send/recv lets rank pairs progress independently,
+            # while the peer-memory path needs a box-wide barrier whose wait adds to the per-rank imbalance
             return "nccl"
         ok, handle = 1, b""
         try:
