@@ -425,7 +425,7 @@ def main():
                                           eps_pri=0.0, eps_dual=0.0, verbose=False, phantom_true=img,
                                           cg_iters=C, tv_sweeps=S, node_prec=node_prec(cfg), device=local,
                                           node_group=args.node_group or None, fuse_pupdate=not args.no_fuse,
-                                          return_engine=True, exchange=args.exchange)
+                                          return_engine=True, exchange=args.exchange, gather="rank0")
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -433,11 +433,11 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         h2d = e2.h2d_bytes
-        d2h = sum(x.nbytes for x in xs) + args.steps * 16 + hist_bytes(hist)
+        d2h = sum(x.nbytes for x in xs if x is not None) + args.steps * 16 + hist_bytes(hist)
         e2e = {"value": args.steps / dt, "unit": "iters/s", "h2d_bytes_per_step": int(h2d / args.steps),
                "d2h_bytes_per_step": int(d2h / args.steps), "call": "block_6_admm_loop_ver2.decentralized_admm(host numpy "
                "sinograms) -> (host x list, history); includes plan build, uploads, A^T b, per-iteration residual "
-               "read-back for the stop test, final x download", "wall_s": round(dt, 3), "iters": len(hist["primal"]),
+               "read-back for the stop test, final x download (to rank 0 when sharded)", "wall_s": round(dt, 3), "iters": len(hist["primal"]),
                "timing_s": {k: round(v, 4) for k, v in hist.get("timing_s", {}).items()}}
         e2.close()
 

@@ -439,8 +439,9 @@ class ADMMEngine:
     def x_local(self):
         return self.x.cpu().numpy()
 
-    def x_all(self):
-        """x of every node on every rank: list of V float32 arrays of length n (views of one pinned host buffer;
+    def x_all(self, gather="all"):
+        """x of every node on every rank (gather="all") or on rank 0 only (gather="rank0": the other ranks get their
+        own nodes' x and None elsewhere, and skip the full device->host copy): list of V float32 arrays of length n (views of one pinned host buffer;
         the reference's are float64 -- `np.stack`, `.reshape(N, N)` and arithmetic behave the same).  When the graph
         is sharded this is a collective (all_gather over NVLink) and every rank returns the full list."""
         torch = self.torch
@@ -462,6 +463,15 @@ class ADMMEngine:
         pad[: self.V] = self.x
         gathered = torch.empty(self.world * mx, self.n, dtype=torch.float32, device=self.dev)
         self.dist.all_gather_into_tensor(gathered, pad, group=self.group)
+        if gather == "rank0" and self.rank != 0:
+            lo = self.rank * mx
+            host[lo:lo + self.V].copy_(gathered[lo:lo + self.V], non_blocking=True)
+            torch.cuda.synchronize(self.dev)
+            arr = host.numpy()
+            out = []
+            for k in range(self.world):
+                out.extend((arr[k * mx + i] if k == self.rank else None) for i in range(counts[k]))
+            return out
         host.copy_(gathered, non_blocking=True)
         torch.cuda.synchronize(self.dev)
         arr = host.numpy()

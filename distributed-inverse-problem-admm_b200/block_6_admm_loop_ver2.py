@@ -48,7 +48,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                        # --- B200 solver controls (not in the reference) ---
                        cg_iters=8, tv_sweeps=1, tv_mu=None, node_prec=None, weighted_z=False, scs_eps=None,
                        check_every=1, node_group=None, fuse_pupdate=True, device=None, return_engine=False,
-                       distributed=None, ax_refresh_every=10, exchange="auto",
+                       distributed=None, ax_refresh_every=10, exchange="auto", gather="all",
                        **kwargs):
     """Returns x_per_node as list of reconstructions, each length n, and the history of residual norms
     (block_6_admm_loop_ver2.py:21-24).
@@ -59,7 +59,8 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
     Under torch.distributed (NCCL) the nodes are sharded over the ranks; every rank returns the full result
     (`distributed=False` keeps the whole graph on this rank's GPU).  `exchange`: "p2p" reads the cut-edge iterates
     straight from the peers' memory over NVLink inside the edge kernel (CUDA IPC), "nccl" uses grouped send/recv,
-    "auto" picks p2p when IPC mapping works on every rank.
+    "auto" picks by rank count.  `gather`: "all" (every rank returns every node's x, like the single-process
+    reference) or "rank0" (only rank 0 receives the full list; the others get their own nodes and None elsewhere).
     """
     for k in list(kwargs):
         if k in _IGNORED:
@@ -112,7 +113,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
     iters = solve(eng, max_iters, eps_pri, eps_dual, verbose=verbose, stop=True, check_every=check_every,
                   snapshot=snapshot if snapshot_dir is not None else None)
     t1 = time.perf_counter()
-    x = eng.x_all()
+    x = eng.x_all(gather)
     t2 = time.perf_counter()
     history = eng.history(iters)
     history["primal_res"], history["dual_res"], history["obj"] = history["primal"], history["dual"], history["obj_total"]
