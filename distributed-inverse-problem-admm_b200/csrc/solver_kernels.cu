@@ -53,7 +53,7 @@ __device__ __forceinline__ void load_seg(const float* __restrict__ row, int c, i
     (void)vec;
 }
 
-__global__ void __launch_bounds__(TVX * TVY)
+__global__ void __launch_bounds__(TVX * TVY, 4)
 tv_fused_kernel(const TvParams P) {
     __shared__ __align__(16) float red[96];
     const int N = P.N;
@@ -374,7 +374,7 @@ __device__ __forceinline__ void edge_elem(const EdgePtrs& e, float zo, float xiv
     s[2] = fmaf(dz, dz, s[2]);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 edge_kernel(const EdgeParams P) {
     __shared__ __align__(16) float red[160];
     const EdgeDesc d = P.edges[blockIdx.y];
