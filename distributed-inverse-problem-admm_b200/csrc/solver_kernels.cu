@@ -216,7 +216,7 @@ cg_update_kernel(const CgParams P) {
     const float* __restrict__ p = P.p + nb;
     const float* __restrict__ hp = P.hp + nb;
     float s = 0.f;
-    const long long n4 = P.n >> 2;
+    const long long n4 = ((P.n & 3) == 0 && (P.stride & 3) == 0) ? (P.n >> 2) : 0;   // float4 only when every node image is 16-byte aligned
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 xv = ld4(x + 4 * i), rv = ld4(rin + 4 * i);
         const float4 pv = ld4(p + 4 * i), hv = ld4(hp + 4 * i);
@@ -227,11 +227,10 @@ cg_update_kernel(const CgParams P) {
         st4(x + 4 * i, xv); st4(r + 4 * i, rv);
         s = fmaf(rv.x, rv.x, s); s = fmaf(rv.y, rv.y, s); s = fmaf(rv.z, rv.z, s); s = fmaf(rv.w, rv.w, s);
     }
-    if (blockIdx.x == 0)
-        for (long long i = 4 * n4 + threadIdx.x; i < P.n; i += blockDim.x) {
-            const float xv = fmaf(alpha, p[i], x[i]), rv = fmaf(-alpha, hp[i], rin[i]);
-            x[i] = xv; r[i] = rv; s = fmaf(rv, rv, s);
-        }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += (long long)gridDim.x * blockDim.x) {
+        const float xv = fmaf(alpha, p[i], x[i]), rv = fmaf(-alpha, hp[i], rin[i]);
+        x[i] = xv; r[i] = rv; s = fmaf(rv, rv, s);
+    }
     float v[1] = {s};
     block_sum<1>(v, red);
     grid_reduce_store<1>(v, P.part + (long long)blockIdx.y * gridDim.x, P.counter + blockIdx.y, blockIdx.x,

@@ -127,3 +127,27 @@ def test_slice_parallel_batch_equals_independent_solves():
         assert np.allclose(pn, np.array(hs["pri_per_node"]), rtol=1e-4)
     # and the union's residual is the root-sum-square of the slices'
     assert len(hb["primal"]) == iters
+
+
+@pytest.mark.parametrize("N,D,det_w,C,fuse", [(30, None, 2.0, 5, True), (30, None, 2.0, 1, True), (27, 41, 2.4, 4, 1),
+                                               (34, 50, 2.0, 3, False)])
+def test_ragged_sizes_and_detectors(N, D, det_w, C, fuse):
+    """Image sides that are not multiples of 4 / of any tile size, D != N detectors (incl. omega > 1), 1-iteration
+    CG: every scalar tail path of the kernels against the oracle."""
+    from admm_b200 import RayTransformCUDA, node_angles
+    from block_6_admm_loop_ver2 import decentralized_admm
+    from oracle import oracle as O
+    M, V, iters = 42, 3, 25
+    thetas = node_angles(M, V, "reference_literal")
+    img = O.shepp_logan(N)
+    ops_o = [O.JosephOperator(N, t, D, det_w) for t in thetas]
+    sinos = [(op.forward(img) + 0.005 * np.random.default_rng(7 + i).standard_normal(op.shape[0]))
+             .reshape(op.nang, op.D).astype(np.float32) for i, op in enumerate(ops_o)]
+    ops_g = [RayTransformCUDA(N, t, D, det_w) for t in thetas]
+    G = O.make_graph("complete", V)
+    Wi, Q = O.make_precisions([op.colnorm2() for op in ops_o], "harmonic")
+    kw = dict(lam_tv=0.01, rho=1.5, max_iters=iters, eps_pri=0.0, eps_dual=0.0, phantom_true=img, tv_sweeps=1,
+              cg_iters=C, tv_mu=0.7)
+    xo, ho = O.decentralized_admm(ops_o, sinos, G, Wi, Q, N, **kw)
+    xg, hg = decentralized_admm(ops_g, sinos, G, Wi, Q, N, verbose=False, fuse_pupdate=fuse, **kw)
+    _compare(hg, ho, xg, xo, img, N, iters)
