@@ -118,9 +118,9 @@ def synth_gpu(cfg, device):
 
 
 def q_provider(Wl):
-    def Q(i, j):  # block_3_graph_and_precisions.py:34-39 (arithmetic mean)
-        return np.maximum(0.5 * (Wl[i] + Wl[j]), 1e-12)
-    return Q
+    """block_3_graph_and_precisions.make_precisions' arithmetic-mean provider (:34-39) over the given W vectors."""
+    import block_3_graph_and_precisions as b3
+    return b3.make_precisions(Wl, q_mode="arithmetic")[1]
 
 
 def algorithmic_bytes(cfg, G, S, C, nonuniform_q):

@@ -89,6 +89,21 @@ class ADMMEngine:
         nnz_loc = sum(deg)
         if Q is None or np.isscalar(Q):
             self.q_uniform = 1.0 if Q is None else float(Q)
+        elif getattr(Q, "_admm_b200_spec", None) is not None:
+            # block_3.make_precisions provider: upload the W vectors once, form Q_ij on the device
+            mode, Wl = Q._admm_b200_spec
+            need = sorted({g for g in self.loc} | {int(sp.nbr_idx[k]) for g in self.loc
+                                                   for k in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1])})
+            wmap = {g: k for k, g in enumerate(need)}
+            Wd = torch.from_numpy(np.stack([np.asarray(Wl[g], dtype=np.float32).reshape(-1) for g in need])).to(self.dev)
+            self.h2d_bytes += Wd.numel() * 4
+            ii = torch.tensor([wmap[g] for g in self.loc for _ in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1])], device=self.dev)
+            jj = torch.tensor([wmap[int(sp.nbr_idx[k])] for g in self.loc
+                               for k in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1])], device=self.dev)
+            Wi_, Wj_ = Wd[ii], Wd[jj]
+            qd = 0.5 * (Wi_ + Wj_) if mode == "arithmetic" else (Wi_ * Wj_) / (Wi_ + Wj_)
+            self.Qdir = torch.clamp_min(qd, 1e-12).contiguous()
+            del Wi_, Wj_, qd
         else:
             qv = []
             for g in self.loc:
@@ -105,7 +120,7 @@ class ADMMEngine:
         if self.Qdir is not None:
             self.rhoD_vec = torch.zeros(V, n, **f32)
             k = 0
-            for li, d in enumerate(deg):
+            for li, d in enumerate(deg):      # neighbour order, like sum(np.stack(neighbor_Qs)) (block_6_ver2:139)
                 for _ in range(d):
                     self.rhoD_vec[li] += self.Qdir[k]
                     k += 1

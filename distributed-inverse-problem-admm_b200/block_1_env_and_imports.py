@@ -1,24 +1,25 @@
-"""Drop-in for block_1_env_and_imports.py:10-18 (small helpers; no cvxpy import)."""
-import math  # noqa: F401
-import os  # noqa: F401
-import pickle  # noqa: F401
-
+"""Drop-in for the reference's block_1_env_and_imports.py: the three array helpers other blocks import from it
+(:10-18), plus the phantom generators that block_2_load_odl_data.py:13 expects to find here.  Imports neither cvxpy
+nor anything else the hot path does not need."""
 import numpy as np
-import networkx as nx  # noqa: F401
 
-from Gen_Sino_Partitioned import ConstIm, randIm  # noqa: F401  (block_2_load_odl_data.py:13 imports them from here)
+from Gen_Sino_Partitioned import ConstIm, randIm  # noqa: F401
 
 
 def vec(img_2d):
-    return img_2d.reshape(-1)
+    """(N, N) image -> length N*N vector, C order (ix*N + iy)."""
+    return np.reshape(img_2d, -1)
 
 
 def unvec(x_vec, N):
-    return x_vec.reshape(N, N)
+    """Inverse of `vec`."""
+    return np.reshape(x_vec, (N, N))
 
 
 def diag_from_column_norms(A_dense):
-    """eta_j = ||A(:, j)||_2^2 -- operator objects answer through the K2b kernel (block_1:16-18)."""
+    """eta_p = ||A(:, p)||_2^2.  Matrix-free operators answer through the K2b kernel (admm_colnorm2); a dense array is
+    reduced with einsum."""
     if hasattr(A_dense, "colnorm2"):
         return A_dense.colnorm2()
-    return np.sum(A_dense * A_dense, axis=0)
+    A = np.asarray(A_dense)
+    return np.einsum("rp,rp->p", A, A)

@@ -36,6 +36,9 @@ def make_precisions(A_dense_list, q_mode="arithmetic"):
             return np.maximum(0.5 * (Wi_list[i] + Wi_list[j]), _EPS)
     else:
         raise ValueError("q_mode must be 'harmonic' or 'arithmetic'")
+    # lets the CUDA engine form Q_ij on the device from the V uploaded W vectors instead of calling back into Python
+    # for every directed edge (same arithmetic, fp32)
+    Qij_diag._admm_b200_spec = (q_mode, Wi_list)
     return Wi_list, Qij_diag
 
 
@@ -135,6 +138,7 @@ def build_pixel_connected_Q_provider(base_dir="saved_operators_Incmp_Span", A_de
             if i == j:
                 return np.zeros(n, dtype=float)
             return Qij_diag(i, j)
+        Qij_diag_masked._admm_b200_spec = Qij_diag._admm_b200_spec
         return G, Wi_list, Qij_diag_masked, None
     q_cache = _precompute_q_cache(V, Qij_diag)
     keep = _build_all_pixel_masks(q_cache, V, n, strategy=strategy, k=k, seed=seed)
