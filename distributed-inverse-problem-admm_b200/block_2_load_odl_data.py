@@ -58,7 +58,8 @@ def load_odl_data(base_dir="saved_operators_Incmp_Span", N=64, num_nodes=5, nois
         noisy = clean + noise_level * op.range.element(rng.normal(0.0, 1.0, size=op.range.shape))
         sinograms.append(noisy.asarray())
     agg_sinogram = np.vstack(sinograms)                      # block_2_test.py:65-66
-    column_norms_all = [np.sqrt(op.colnorm2()) for op in ray_transforms]   # np.linalg.norm(A_i, axis=0), :62
+    Wi_list = [np.maximum(op.colnorm2(), 1e-12) for op in ray_transforms]   # block_3...:22-23 (data_block2.pkl key)
+    column_norms_all = [np.sqrt(w) for w in Wi_list]                        # np.linalg.norm(A_i, axis=0), :62
     if output_dir is None:
         output_dir = f"Recon_Op_ADMM_{datetime.now().strftime('%Y%m%d_%H%M%S')}"
     if save_operators_dir is not None:
@@ -68,6 +69,7 @@ def load_odl_data(base_dir="saved_operators_Incmp_Span", N=64, num_nodes=5, nois
         "ray_transforms": ray_transforms,
         "sinograms": sinograms,
         "column_norms_all": column_norms_all,
+        "Wi_list": Wi_list,
         "N": N,
         "num_nodes": num_nodes,
         "agg_ray_trafo": agg_ray_trafo,

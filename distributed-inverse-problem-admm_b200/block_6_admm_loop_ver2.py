@@ -116,7 +116,10 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
     x = eng.x_all(gather)
     t2 = time.perf_counter()
     history = eng.history(iters)
+    # aliases used by the skeleton (block_6_admm_loop.py:101-105) and by the older drivers (block_7_main_ver0/1)
     history["primal_res"], history["dual_res"], history["obj"] = history["primal"], history["dual"], history["obj_total"]
+    for key in ("pri_per_node", "dual_per_node", "obj_per_node", "obj_total"):
+        history[key + "_history"] = history[key]
     history["wall_time_s"] = time.perf_counter() - t0
     history["timing_s"] = {"setup": t0 - t_start, "iterations": t1 - t0, "download_x": t2 - t1,
                            "history": time.perf_counter() - t2}

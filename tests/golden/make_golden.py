@@ -256,3 +256,36 @@ out["b6_params"] = np.array([N6, M6, LOOP["S"], LOOP["C"], LOOP["mu"], 0.02, 2.0
 np.savez_compressed(os.path.join(HERE, "reference_golden.npz"), **out)
 print("wrote", os.path.join(HERE, "reference_golden.npz"), len(out), "arrays,",
       os.path.getsize(os.path.join(HERE, "reference_golden.npz")), "bytes")
+
+# ---- call-compatibility facts: how the reference's drivers call the boundary functions -------------------------
+# (keyword names passed, history keys indexed) extracted from the reference sources with `ast`; the CPU tests check
+# that the drop-in modules accept exactly these calls.
+import ast  # noqa: E402
+import json  # noqa: E402
+
+BOUNDARY = ("load_odl_data", "build_pixel_connected_Q_provider", "decentralized_admm", "build_node_problem",
+            "make_precisions", "generate_sinogram", "kt_subgrad_isotropic_tv_from_x", "edge_map_from_vector")
+facts = {"calls": [], "history_keys": [], "data_keys": []}
+for fn in sorted(os.listdir(REF)):
+    if not fn.endswith(".py"):
+        continue
+    try:
+        tree = ast.parse(open(os.path.join(REF, fn)).read())
+    except SyntaxError:
+        continue
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call):
+            name = node.func.id if isinstance(node.func, ast.Name) else getattr(node.func, "attr", None)
+            if name in BOUNDARY:
+                facts["calls"].append({"file": fn, "line": node.lineno, "func": name, "n_positional": len(node.args),
+                                       "keywords": sorted(k.arg for k in node.keywords if k.arg)})
+        if isinstance(node, ast.Subscript) and isinstance(node.value, ast.Name) and isinstance(node.slice, ast.Constant) \
+                and isinstance(node.slice.value, str):
+            if node.value.id in ("hist", "history"):
+                facts["history_keys"].append(node.slice.value)
+            if node.value.id == "data":
+                facts["data_keys"].append(node.slice.value)
+facts["history_keys"] = sorted(set(facts["history_keys"]))
+facts["data_keys"] = sorted(set(facts["data_keys"]))
+json.dump(facts, open(os.path.join(HERE, "reference_call_facts.json"), "w"), indent=1)
+print("wrote reference_call_facts.json:", len(facts["calls"]), "calls,", facts["history_keys"], facts["data_keys"])

@@ -156,3 +156,40 @@ def test_operator_shapes_without_device():
     z = op.domain.zero()
     z.asarray().flat[5] = 1.0
     assert z.asarray().sum() == 1.0
+
+
+def test_boundary_accepts_every_call_the_reference_makes():
+    """tests/golden/reference_call_facts.json lists (via ast, from the reference sources) every call the reference's
+    drivers and test scripts make to the boundary functions; the drop-in modules must bind all of them."""
+    import inspect
+    import json
+    import block_2_load_odl_data as b2
+    import block_3_graph_and_precisions as b3
+    import block_4_tv_helpers as b4
+    import block_4_tv_helpers_with_plot as b4p
+    import block_5_node_problem as b5
+    import block_6_admm_loop as b6s
+    import block_6_admm_loop_ver2 as b6
+    import Gen_Sino_Partitioned as gs
+    facts = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_call_facts.json")))
+    table = {"load_odl_data": b2.load_odl_data, "build_pixel_connected_Q_provider": b3.build_pixel_connected_Q_provider,
+             "make_precisions": b3.make_precisions, "build_node_problem": b5.build_node_problem,
+             "decentralized_admm": b6.decentralized_admm, "generate_sinogram": gs.generate_sinogram,
+             "kt_subgrad_isotropic_tv_from_x": b4.kt_subgrad_isotropic_tv_from_x,
+             "edge_map_from_vector": b4p.edge_map_from_vector}
+    assert b6s.decentralized_admm is b6.decentralized_admm
+    assert len(facts["calls"]) >= 25
+    for c in facts["calls"]:
+        f = table[c["func"]]
+        kws = {k: None for k in c["keywords"]}
+        inspect.signature(f).bind(*([None] * c["n_positional"]), **kws)        # raises TypeError on a mismatch
+        if c["func"] == "decentralized_admm":                                   # **kwargs are filtered at run time
+            named = set(inspect.signature(f).parameters) | set(b6._IGNORED)
+            assert set(c["keywords"]) <= named, (c["file"], c["line"], set(c["keywords"]) - named)
+    produced = set(b6s.__dict__["decentralized_admm"].__code__.co_consts) | set(admm_b200.solver.HIST_KEYS) | {
+        "primal_res", "dual_res", "obj", "pri_per_node_history", "dual_per_node_history", "obj_per_node_history",
+        "obj_total_history"}
+    assert set(facts["history_keys"]) <= produced, set(facts["history_keys"]) - produced
+    src = open(os.path.join(ROOT, "distributed-inverse-problem-admm_b200", "block_2_load_odl_data.py")).read()
+    for key in facts["data_keys"]:
+        assert f'"{key}"' in src, key
