@@ -4,7 +4,7 @@ Python here is plumbing (device memory via PyTorch, streams, torch.distributed);
 of the path runs in the hand-written sm_100a kernels of libadmm_b200.so (csrc/), called through the C ABI
 declared in include/admm_b200.h.  There is no CPU fallback.
 """
-from . import _native  # noqa: F401
+from . import _native, registry  # noqa: F401
 from .geometry import (angle_split, default_angles_total, graph_csr, make_graph, node_angles, node_to_gpu,  # noqa: F401
                        psnr, shepp_logan, trig_table32)
 from .operators import DiscreteSpace, Element, Plan, RayTransformCUDA, stack_operators  # noqa: F401

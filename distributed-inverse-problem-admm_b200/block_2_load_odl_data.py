@@ -9,7 +9,7 @@ from datetime import datetime
 
 import numpy as np
 
-from admm_b200 import RayTransformCUDA, angle_split, default_angles_total, node_angles, stack_operators
+from admm_b200 import RayTransformCUDA, angle_split, default_angles_total, node_angles, registry, stack_operators
 from Gen_Sino_Partitioned import ConstIm, randIm  # noqa: F401
 
 
@@ -62,8 +62,9 @@ def load_odl_data(base_dir="saved_operators_Incmp_Span", N=64, num_nodes=5, nois
     column_norms_all = [np.sqrt(w) for w in Wi_list]                        # np.linalg.norm(A_i, axis=0), :62
     if output_dir is None:
         output_dir = f"Recon_Op_ADMM_{datetime.now().strftime('%Y%m%d_%H%M%S')}"
-    if save_operators_dir is not None:
-        os.makedirs(save_operators_dir, exist_ok=True)
+    for key in (base_dir, save_operators_dir):      # what the reference pickles into these directories
+        if key is not None:
+            registry.put(key, ray_transforms)
     return {
         "A_dense_list": ray_transforms,          # matrix-free: .shape, @, .T, .colnorm2()
         "ray_transforms": ray_transforms,

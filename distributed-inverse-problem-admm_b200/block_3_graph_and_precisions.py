@@ -124,11 +124,15 @@ def build_pixel_connected_Q_provider(base_dir="saved_operators_Incmp_Span", A_de
     if A_dense_list is None:
         import os
         import pickle
+        from admm_b200 import registry
+        A_dense_list = registry.get(base_dir)          # operators block_2.load_odl_data built for this base_dir
         A_path = os.path.join(base_dir, A_dense_list_pickle)
-        if not os.path.exists(A_path):
-            raise FileNotFoundError(f"A_dense_list pickle not found at {A_path}; pass A_dense_list=<operators>")
-        with open(A_path, "rb") as f:
-            A_dense_list = pickle.load(f)
+        if A_dense_list is None and os.path.exists(A_path):
+            with open(A_path, "rb") as f:
+                A_dense_list = pickle.load(f)
+        if A_dense_list is None:
+            raise FileNotFoundError(f"no operators registered for {base_dir!r} and no pickle at {A_path}; call "
+                                    "load_odl_data(base_dir=...) first or pass A_dense_list=<operators>")
     Wi_list, Qij_diag = make_precisions(A_dense_list, q_mode=q_mode)
     V, n = len(Wi_list), Wi_list[0].shape[0]
     if strategy in ("ring", "regular", "er", "complete", "path"):

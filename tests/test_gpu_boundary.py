@@ -174,3 +174,22 @@ def test_block3_provider_fast_path_equals_callable_path():
         x2, h2 = decentralized_admm(ops, sinos, G, Wi, lambda i, j: Q(i, j), N, **kw)   # plain callable: no spec
         assert np.allclose(h1["primal"], h2["primal"], rtol=1e-5) and np.allclose(h1["obj_total"], h2["obj_total"], rtol=1e-5)
         assert max(np.linalg.norm(a - b) / np.linalg.norm(b) for a, b in zip(x1, x2)) < 1e-5
+
+
+def test_block7_main_driver_end_to_end(tmp_path):
+    """The live driver's flow (block_7_main_ver3.py:332-371 settings, fewer iterations): base_dir hand-over from
+    block_2 to block_3, per-pixel kNN masks, snapshots, run_parameters.txt and every history dump."""
+    import block_7_main_ver3 as b7
+    np.random.seed(1)
+    x_list, hist = b7.main(N=32, num_nodes=5, max_iters=20, out_root=str(tmp_path), snapshot_div=2)
+    out = tmp_path / "knn_k2"
+    assert (out / "run_parameters.txt").exists()
+    for name in ("obj_per_node", "obj_total", "pri_per_node", "dual_per_node", "primal_hist", "dual_hist",
+                 "sino_mse_per_node", "sino_mse_total", "img_mse_per_node", "img_mse_total"):
+        assert (out / f"knn_k2_{name}.npy").exists(), name
+    assert (out / "knn_k2_node_4.npy").exists() and np.load(out / "knn_k2_node_0.npy").shape == (32, 32)
+    iters = len(hist["primal"])
+    assert 1 <= iters <= 20 and np.load(out / "knn_k2_pri_per_node.npy").shape == (iters, 5)
+    snaps = sorted(p.name for p in (out / "snapshots").glob("iter_*_node_0.npy"))
+    assert snaps and all(int(s.split("_")[1]) % 10 == 0 for s in snaps)          # snapshot_every = max_iters // 2
+    assert len(x_list) == 5
