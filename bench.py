@@ -345,6 +345,7 @@ def main():
     nat.profile_enable(prof_inline)
     if prof_inline:
         nat.profile_read()
+    eng.time_exchange = world > 1
     clocks = ClockSampler(local) if rank == 0 else None
     l0 = nat.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -384,6 +385,11 @@ def main():
         launches = int(lt.item())
     ms_per_step = ms / args.steps
     value = 1e3 / ms_per_step
+    exch = None
+    if world > 1 and getattr(eng, "exchange_events", None):
+        tot = sum(a.elapsed_time(b) for a, b in eng.exchange_events[-args.steps:])
+        exch = {"pack_tv_localedges_and_exposed_exchange_ms_per_step": round(tot / args.steps, 4), "mode": eng.exchange_mode,
+                "cut_edge_ends_this_rank": eng.n_pack, "bytes_out_per_step": eng.n_pack * eng.n * 4}
     pri, dual = eng.residuals()
     eng_iters = eng.k
 
@@ -482,7 +488,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg, G),
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
-                "iteration_roofline": it_roof, "cpu_baseline": cpu, "kernels": kernels,
+                "iteration_roofline": it_roof, "exchange": exch, "cpu_baseline": cpu, "kernels": kernels,
                 "residuals_after": {"primal": pri, "dual": dual, "iterations": eng_iters}}
         print(json.dumps(line), flush=True)
     if world > 1:

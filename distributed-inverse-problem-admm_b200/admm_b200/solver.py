@@ -390,6 +390,12 @@ class ADMMEngine:
             self.dist.all_reduce(self._bar, group=self.group)
         for r in reqs:
             r.wait()          # stream-level wait: the compute stream now depends on the received buffers
+        if getattr(self, "_edges_timed", None):
+            # pack + TV + local edges + whatever of the exchange they did not hide (bench diagnostics)
+            ea, eb = self._edges_timed
+            eb.record()
+            self.exchange_events = getattr(self, "exchange_events", []) + [(ea, eb)]
+            self._edges_timed = None
         if E - nl:
             nat.check(L.admm_edge_update(h, sref, desc.data_ptr() + nl * esz, E - nl,
                                          self.sums.data_ptr() + nl * 5 * 8, self._stream()), "admm_edge_update")
@@ -406,8 +412,14 @@ class ADMMEngine:
         self.nodes_phase()
         reqs = ()
         if self.world > 1:
+            timed = getattr(self, "time_exchange", False)
+            if timed:
+                ea, eb = (self.torch.cuda.Event(enable_timing=True) for _ in range(2))
+                ea.record()
             reqs = self.exchange_start()      # x is final: the exchange runs under the TV pass and the local edges
             self.tv_phase()
+            if timed:
+                self._edges_timed = (ea, eb)
         self.edges_phase(reqs)
         self.k += 1
 

@@ -151,3 +151,53 @@ def test_ragged_sizes_and_detectors(N, D, det_w, C, fuse):
     xo, ho = O.decentralized_admm(ops_o, sinos, G, Wi, Q, N, **kw)
     xg, hg = decentralized_admm(ops_g, sinos, G, Wi, Q, N, verbose=False, fuse_pupdate=fuse, **kw)
     _compare(hg, ho, xg, xo, img, N, iters)
+
+
+def test_single_node_without_edges_and_isolated_node():
+    """Empty edge set (V = 1) and a graph with an isolated node: the loop degenerates to independent TV-regularised
+    least-squares solves; residuals of an edgeless graph are exactly 0."""
+    import networkx as nx
+    from admm_b200 import RayTransformCUDA, node_angles
+    from block_6_admm_loop_ver2 import decentralized_admm
+    from oracle import oracle as O
+    N = 32
+    thetas = node_angles(60, 3)
+    img = O.shepp_logan(N)
+    ops_o = [O.JosephOperator(N, t) for t in thetas]
+    sinos = [op.forward(img).reshape(op.nang, N).astype(np.float32) for op in ops_o]
+    kw = dict(lam_tv=0.01, rho=1.0, max_iters=12, eps_pri=-1.0, eps_dual=-1.0, phantom_true=img, cg_iters=6, tv_mu=1.0)
+    G1 = nx.Graph()
+    G1.add_node(0)
+    x1, h1 = decentralized_admm([RayTransformCUDA(N, thetas[0])], sinos[:1], G1, None, None, N, verbose=False, **kw)
+    xo, ho = O.decentralized_admm(ops_o[:1], sinos[:1], G1, None, None, N, uniform_q=1.0, **kw)
+    assert h1["primal"] == [0.0] * 12 and h1["dual"] == [0.0] * 12
+    assert np.linalg.norm(x1[0] - xo[0]) < 1e-3 * np.linalg.norm(xo[0])
+    assert np.allclose(h1["mse_sino_total"], ho["mse_sino_total"], rtol=2e-3)
+    G3 = nx.Graph()
+    G3.add_nodes_from(range(3))
+    G3.add_edge(0, 2)                                     # node 1 is isolated
+    x3, h3 = decentralized_admm([RayTransformCUDA(N, t) for t in thetas], sinos, G3, None, None, N, verbose=False, **kw)
+    xo3, ho3 = O.decentralized_admm(ops_o, sinos, G3, None, None, N, uniform_q=1.0, **kw)
+    assert np.allclose(h3["primal"], ho3["primal"], rtol=1e-3) and np.allclose(h3["dual"], ho3["dual"], rtol=1e-3)
+    for i in range(3):
+        assert np.linalg.norm(x3[i] - xo3[i]) < 1e-3 * np.linalg.norm(xo3[i])
+    assert h3["pri_per_node"][-1][1] == 0.0
+
+
+def test_cfg2_size_parity_few_iterations():
+    """BASELINE configs[1] at full size (512^2, 360 angles, 16 nodes, random 4-regular graph, uniform precisions):
+    the first outer iterations against the oracle."""
+    from admm_b200 import RayTransformCUDA, node_angles
+    from block_6_admm_loop_ver2 import decentralized_admm
+    from oracle import oracle as O
+    N, M, V, iters = 512, 360, 16, 4
+    thetas = node_angles(M, V)
+    img = O.shepp_logan(N)
+    ops_o = [O.JosephOperator(N, t) for t in thetas]
+    sinos = [(op.forward(img) + 0.005 * np.random.default_rng(1234 + i).standard_normal(op.shape[0]))
+             .reshape(op.nang, N).astype(np.float32) for i, op in enumerate(ops_o)]
+    G = O.make_graph("regular", V, seed=0, degree=4)
+    kw = dict(lam_tv=0.02, rho=2.0, max_iters=iters, eps_pri=0.0, eps_dual=0.0, phantom_true=img, cg_iters=8)
+    xo, ho = O.decentralized_admm(ops_o, sinos, G, None, None, N, uniform_q=1.0, **kw)
+    xg, hg = decentralized_admm([RayTransformCUDA(N, t) for t in thetas], sinos, G, None, None, N, verbose=False, **kw)
+    _compare(hg, ho, xg, xo, img, N, iters)
