@@ -109,17 +109,25 @@ fwd_strip_kernel(const FwdParams P) {
         if (writer) pout[g] = pn;
         return pn;
     };
-    auto fuse4 = [&](long long g, float4 pold) -> float4 {
-        if (mode == 0) return pold;
-        float4 rv = ld4(rimg + g);
+    // vector form split into (all loads) / (update + stores) so that two items' loads are in flight together
+    struct Item4 { float4 p, r, h, x; };
+    auto load4 = [&](long long g) -> Item4 {
+        Item4 it;
+        it.p = ld4(img + g);
+        if (mode != 0) it.r = ld4(rimg + g);
+        if (mode == 2) { it.h = ld4(hpimg + g); if (writer) it.x = ld4(xio + g); }
+        return it;
+    };
+    auto finish4 = [&](long long g, const Item4& it) -> float4 {
+        if (mode == 0) return it.p;
+        float4 rv = it.r;
         if (mode == 2) {
-            const float4 hv = ld4(hpimg + g);
-            rv.x = fmaf(-alpha, hv.x, rv.x); rv.y = fmaf(-alpha, hv.y, rv.y);
-            rv.z = fmaf(-alpha, hv.z, rv.z); rv.w = fmaf(-alpha, hv.w, rv.w);
+            rv.x = fmaf(-alpha, it.h.x, rv.x); rv.y = fmaf(-alpha, it.h.y, rv.y);
+            rv.z = fmaf(-alpha, it.h.z, rv.z); rv.w = fmaf(-alpha, it.h.w, rv.w);
             if (writer) {
-                float4 xv = ld4(xio + g);
-                xv.x = fmaf(alpha, pold.x, xv.x); xv.y = fmaf(alpha, pold.y, xv.y);
-                xv.z = fmaf(alpha, pold.z, xv.z); xv.w = fmaf(alpha, pold.w, xv.w);
+                float4 xv = it.x;
+                xv.x = fmaf(alpha, it.p.x, xv.x); xv.y = fmaf(alpha, it.p.y, xv.y);
+                xv.z = fmaf(alpha, it.p.z, xv.z); xv.w = fmaf(alpha, it.p.w, xv.w);
                 st4(xio + g, xv);
                 st4(rout + g, rv);
                 rsum = fmaf(rv.x, rv.x, rsum); rsum = fmaf(rv.y, rv.y, rsum);
@@ -127,11 +135,12 @@ fwd_strip_kernel(const FwdParams P) {
             }
         }
         float4 pn;
-        pn.x = fmaf(beta, pold.x, rv.x); pn.y = fmaf(beta, pold.y, rv.y);
-        pn.z = fmaf(beta, pold.z, rv.z); pn.w = fmaf(beta, pold.w, rv.w);
+        pn.x = fmaf(beta, it.p.x, rv.x); pn.y = fmaf(beta, it.p.y, rv.y);
+        pn.z = fmaf(beta, it.p.z, rv.z); pn.w = fmaf(beta, it.p.w, rv.w);
         if (writer) st4(pout + g, pn);
         return pn;
     };
+    const bool vec4 = ((N & 3) == 0);
 
     const int slot = tid / FTPA, t = tid % FTPA;
     const int nslab = (Kseg + FL - 1) / FL;
@@ -151,35 +160,47 @@ fwd_strip_kernel(const FwdParams P) {
                                    __float_as_int((float)(base - fbase)));
         }
         // ---- stage tile -------------------------------------------------------------------------
-        if (xdom) {
-            // pixel (ix = U0+u, iy = K0+k): contiguous along k.  thread -> (u, 4 consecutive k)
-            for (int idx = tid; idx < FW * (FL / 4); idx += FTHREADS) {
-                const int u = idx / (FL / 4), k4 = (idx % (FL / 4)) * 4;
-                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (u < Wt) {
-                    const long long g = (long long)(U0 + u) * N + K0 + k4;
-                    if (k4 + 3 < Lt && ((N & 3) == 0)) {
-                        val = fuse4(g, ld4(img + g));
-                    } else {
-                        float tmp[4] = {0.f, 0.f, 0.f, 0.f};
-                        for (int i = 0; i < 4; ++i)
-                            if (k4 + i < Lt) tmp[i] = fuse1(g + i, img[g + i]);
-                        val = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
-                    }
+        // x-dominant: pixel (ix = U0+u, iy = K0+k) is contiguous along the step axis k -> item = (u, 4 consecutive k),
+        //             stored transposed (stride FPITCH, odd -> conflict-free up to 2-way);
+        // y-dominant: pixel (ix = K0+k, iy = U0+u) is contiguous along the interpolation axis u -> item = (k, 4 u).
+        {
+            const int per_row = xdom ? (FL / 4) : (FW / 4);            // float4 items per contiguous run
+            const int nitems = xdom ? FW * (FL / 4) : FL * (FW / 4);
+            auto decode = [&](int idx, int& row, int& c4, bool& full, bool& any, long long& g) {
+                row = idx / per_row;                                    // u (x-dom) or k (y-dom)
+                c4 = (idx % per_row) * 4;                               // k4 (x-dom) or u4 (y-dom)
+                const int rlim = xdom ? Wt : Lt, clim = xdom ? Lt : Wt;
+                any = (idx < nitems) && row < rlim && c4 < clim;
+                full = any && vec4 && (c4 + 3 < clim);
+                g = xdom ? (long long)(U0 + row) * N + K0 + c4 : (long long)(K0 + row) * N + U0 + c4;
+            };
+            auto store = [&](int row, int c4, float4 val) {
+                if (xdom) {
+                    float* dst = S + c4 * FPITCH + FHALO + row;
+                    dst[0] = val.x; dst[FPITCH] = val.y; dst[2 * FPITCH] = val.z; dst[3 * FPITCH] = val.w;
+                } else {
+                    float* dst = S + row * FPITCH + FHALO + c4;
+                    dst[0] = val.x; dst[1] = val.y; dst[2] = val.z; dst[3] = val.w;
                 }
-                float* dst = S + k4 * FPITCH + FHALO + u;
-                dst[0] = val.x; dst[FPITCH] = val.y; dst[2 * FPITCH] = val.z; dst[3 * FPITCH] = val.w;
-            }
-        } else {
-            // pixel (ix = K0+k, iy = U0+u): contiguous along u
-            for (int idx = tid; idx < FL * FW; idx += FTHREADS) {
-                const int k = idx / FW, u = idx % FW;
-                float x = 0.f;
-                if (k < Lt && u < Wt) {
-                    const long long g = (long long)(K0 + k) * N + U0 + u;
-                    x = fuse1(g, img[g]);
+            };
+            auto tail = [&](long long g, int c4, bool any) -> float4 {   // ragged / unaligned items, element by element
+                float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+                if (any) {
+                    const int clim = xdom ? Lt : Wt;
+                    for (int i = 0; i < 4; ++i)
+                        if (c4 + i < clim) tmp[i] = fuse1(g + i, img[g + i]);
                 }
-                S[k * FPITCH + FHALO + u] = x;
+                return make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+            };
+            for (int idx = tid; idx < nitems; idx += FTHREADS) {
+                int rowA, cA;
+                bool fullA, anyA;
+                long long gA;
+                decode(idx, rowA, cA, fullA, anyA, gA);
+                float4 va;
+                if (fullA) { const Item4 a = load4(gA); va = finish4(gA, a); }
+                else va = tail(gA, cA, anyA);
+                store(rowA, cA, va);
             }
         }
         for (int k = tid; k < FL; k += FTHREADS) {
