@@ -18,6 +18,8 @@ namespace admm {
 // per slab -> no atomics).  At the end the rows are stored as fixed-size records; fwd_reduce_kernel sums
 // the records of all strips/segments in a fixed order (deterministic) and applies the step weight.
 // =================================================================================================
+constexpr bool kPrefetchNextSlab = false;
+
 __global__ void __launch_bounds__(FTHREADS, 4)
 fwd_strip_kernel(const FwdParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -212,7 +214,7 @@ fwd_strip_kernel(const FwdParams P) {
         }
         __syncthreads();
         // ---- pull the next slab's operands towards L2 while this slab is sampled (staging is latency-bound) ----
-        if (slab + 1 < nslab) {
+        if (kPrefetchNextSlab && slab + 1 < nslab) {
             const int K1 = K0 + FL;
             if (xdom) {
                 for (int idx = tid; idx < FW * (FL / 32); idx += FTHREADS) {   // one 128-byte line per request

@@ -201,3 +201,42 @@ def test_cfg2_size_parity_few_iterations():
     xo, ho = O.decentralized_admm(ops_o, sinos, G, None, None, N, uniform_q=1.0, **kw)
     xg, hg = decentralized_admm([RayTransformCUDA(N, t) for t in thetas], sinos, G, None, None, N, verbose=False, **kw)
     _compare(hg, ho, xg, xo, img, N, iters)
+
+
+def test_cfg4_size_iteration_is_deterministic_and_self_consistent():
+    """BASELINE configs[3] at full size (2048^2, 720 angles, 64 nodes, ER graph): two runs are bit-identical (no float
+    atomics anywhere), the history obeys the identities of block_6_admm_loop_ver2.py:232-264, and the first iterate
+    is the Tikhonov-like CG solution the oracle gives for one node."""
+    from admm_b200 import RayTransformCUDA, make_graph, node_angles, shepp_logan
+    from block_6_admm_loop_ver2 import decentralized_admm
+    from oracle import oracle as O
+    N, M, V = 2048, 720, 64
+    thetas = node_angles(M, V)
+    img = shepp_logan(N)
+    ops = [RayTransformCUDA(N, t) for t in thetas]
+    import torch
+    from admm_b200 import Plan
+    plan = Plan(N, thetas)
+    d_s = torch.zeros(plan.A, N, device="cuda")
+    plan.forward(torch.from_numpy(img.astype(np.float32).reshape(1, -1)).cuda().repeat(V, 1), d_s)
+    s = d_s.cpu().numpy()
+    plan.close()
+    sinos = [s[plan.ang_ptr[i]:plan.ang_ptr[i + 1]] for i in range(V)]
+    G = make_graph("er", V, seed=0, p=0.1)
+    kw = dict(lam_tv=0.02, rho=2.0, max_iters=3, eps_pri=0.0, eps_dual=0.0, verbose=False, phantom_true=img, cg_iters=8)
+    x1, h1 = decentralized_admm(ops, sinos, G, None, None, N, **kw)
+    x2, h2 = decentralized_admm(ops, sinos, G, None, None, N, **kw)
+    assert h1["primal"] == h2["primal"] and h1["dual"] == h2["dual"]
+    assert all(np.array_equal(a, b) for a, b in zip(x1, x2))
+    for k in range(3):
+        pn, dn = np.array(h1["pri_per_node"][k]), np.array(h1["dual_per_node"][k])
+        assert abs(np.sum(pn ** 2) - h1["primal"][k] ** 2) <= 1e-9 * h1["primal"][k] ** 2      # r2 = sum_i pri_node[i]
+        assert abs(np.sum(dn ** 2) - 2 * h1["dual"][k] ** 2) <= 1e-9 * h1["dual"][k] ** 2     # each edge feeds 2 nodes
+        assert abs(h1["mse_sino_total"][k] - np.sum(h1["mse_sino_per_node"][k])) < 1e-9 * h1["mse_sino_total"][k]
+    # one node of the first iteration against the oracle (z = y = 0: a single CG solve from x = 0)
+    i = 37
+    op = O.JosephOperator(N, thetas[i])
+    x, d, w = np.zeros(N * N), np.zeros(2 * N * N), np.zeros(2 * N * N)
+    O.x_update(op, 1.0, op.adjoint(sinos[i].reshape(-1).astype(np.float64)), 2.0 * G.degree(i), 2.0, 0.02, 1, 8, x, d, w)
+    xg, hg = decentralized_admm(ops, sinos, G, None, None, N, **dict(kw, max_iters=1))
+    assert np.linalg.norm(xg[i] - x) < 1e-3 * np.linalg.norm(x)
