@@ -269,7 +269,7 @@ def workload_config(args, cfg, G):
          "cg_iters": args.cg_iters, "noise_sigma": SIGMA, "partition": "contiguous",
          "inputs_larger_than_L2": True, "stop_test": "disabled in the timed region"}
     if args.gpus > 1:
-        c["parallelism"] = f"graph nodes sharded over {args.gpus} GPUs, cut-edge exchange={getattr(args, 'exchange_used', args.exchange)}"
+        c["parallelism"] = f"graph nodes sharded over {args.gpus} GPUs, cut-edge exchange={getattr(args, 'exchange_used', args.exchange)}" + (f" in {args.phases_used} phases" if getattr(args, "phases_used", 1) > 1 else "")
     if G is not None:
         c["edges"] = G.number_of_edges()
     return c
@@ -287,7 +287,9 @@ def main():
     ap.add_argument("--node-group", type=int, default=0)
     ap.add_argument("--slices", type=int, default=0, help="override the slice count of cfg5")
     ap.add_argument("--no-fuse", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "push", "nccl"])
+    ap.add_argument("--exchange-phases", type=int, default=None,
+                    help="NCCL exchange: post the cut-edge transfers in this many pieces per iteration (default 2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="no per-kernel CUDA events in the timed region")
@@ -326,9 +328,10 @@ def main():
     eng = ADMMEngine(thetas, sinos, G, cfg["N"], lam_tv=LAM, rho=RHO, Q=Q, Wi_list=Wl, node_prec=node_prec(cfg),
                      tv_sweeps=S, cg_iters=C, phantom_true=img, device=local, dist=dist if world > 1 else None,
                      rank=rank, world=world, node_group=args.node_group or None, fuse_pupdate=not args.no_fuse,
-                     max_iters=total, exchange=args.exchange)
+                     max_iters=total, exchange=args.exchange, exchange_phases=args.exchange_phases)
 
-    args.exchange_used = eng.exchange_mode
+    args.exchange_used = "push" if (eng.exchange_mode == "p2p" and getattr(eng, "_push", False)) else eng.exchange_mode
+    args.phases_used = eng.phases
 
     def barrier():
         if world > 1:
@@ -462,7 +465,8 @@ def main():
                                           eps_pri=0.0, eps_dual=0.0, verbose=False, phantom_true=img,
                                           cg_iters=C, tv_sweeps=S, node_prec=node_prec(cfg), device=local,
                                           node_group=args.node_group or None, fuse_pupdate=not args.no_fuse,
-                                          return_engine=True, exchange=args.exchange, gather="rank0")
+                                          return_engine=True, exchange=args.exchange, gather="rank0",
+                                          exchange_phases=args.exchange_phases)
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:

@@ -79,6 +79,8 @@ def lib():
     L.admm_plan_destroy.restype = None
     L.admm_plan_info.restype = ll
     L.admm_plan_info.argtypes = [vp, i]
+    L.admm_plan_set.restype = i
+    L.admm_plan_set.argtypes = [vp, i, ll]
     L.admm_forward.argtypes = [vp, vp, ll, i, i, vp, vp]
     L.admm_adjoint.argtypes = [vp, vp, vp, vp, ll, i, i, vp]
     L.admm_colnorm2.argtypes = [vp, vp, ll, i, i, vp]
@@ -109,10 +111,12 @@ def lib():
 
 
 EXPORTS = ("admm_version", "admm_last_error", "admm_device_count", "admm_plan_create", "admm_plan_destroy",
-           "admm_plan_info", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host",
+           "admm_plan_info", "admm_plan_set", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host",
            "admm_adjoint_host", "admm_colnorm2_host", "admm_rhs0", "admm_x_update", "admm_edge_update", "admm_pack", "admm_finalize",
            "admm_tv_pass", "admm_launch_count", "admm_profile_enable", "admm_profile_read", "admm_grad2d_host",
            "admm_div2d_host", "admm_kt_subgrad_host", "admm_ipc_alloc", "admm_ipc_open", "admm_ipc_close", "admm_ipc_free")
+
+OPT_PACK_BLOCKS = 0
 
 KC_NAMES = ("fwd", "fwd_reduce", "back_plain", "back_hp", "back_resid0", "colnorm2", "tv", "cg_update", "p_update",
             "sino_axpy", "sino_resid", "rhs0", "edge", "pack", "finalize", "fwd_fused")

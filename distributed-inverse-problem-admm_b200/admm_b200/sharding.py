@@ -25,7 +25,10 @@ class LocalEdge:
     owns_dual: bool   # this rank adds s2 / dual_node for the edge
     slot: int = 0     # index into this rank's edge arrays
     peer: int = -1    # owner of the remote end (cut edges)
-    xslot: int = -1   # index into the exchange buffers of `peer`
+    xslot: int = -1   # index into the exchange buffers of `peer` (phases == 1: same row both ways)
+    sslot: int = -1   # row of this rank's a in send[peer]  (ordered by the phase of the LOCAL end's node)
+    rslot: int = -1   # row of the peer's a in recv[peer]     (ordered by the phase of the REMOTE end's node)
+    sphase: int = 0   # exchange phase in which this rank's end is sent
 
 
 @dataclass
@@ -45,16 +48,36 @@ class ShardPlan:
     eslot: dict = field(default_factory=dict)       # global edge id -> local slot
     peers: list = field(default_factory=list)       # ascending peer ranks this rank exchanges with
     exch: dict = field(default_factory=dict)        # peer -> [global edge ids] ascending (same list on both sides)
+    phases: int = 1                                 # the exchange is posted in this many pieces per iteration
+    node_phase: dict = field(default_factory=dict)  # global node id -> phase of its owner's x-update schedule
+    send_rows: dict = field(default_factory=dict)   # peer -> [phases+1] row offsets into send[peer]
+    recv_rows: dict = field(default_factory=dict)   # peer -> [phases+1] row offsets into recv[peer]
 
     @property
     def n_cut(self):
         return sum(len(v) for v in self.exch.values())
 
 
-def build_shard_plan(G, world: int, rank: int) -> ShardPlan:
+def phase_bounds(count: int, phases: int) -> list:
+    """Local-node index ranges of the x-update phases: phase k = [b[k], b[k+1]) (contiguous, sizes differ by <= 1)."""
+    return [-((-k * count) // phases) for k in range(phases)] + [count]
+
+
+def build_shard_plan(G, world: int, rank: int, phases: int = 1) -> ShardPlan:
+    """phases > 1: every rank runs its x-updates in `phases` contiguous node blocks and posts the a = x + y of a
+    block's cut-edge ends as soon as the block is done, so the transfer hides behind the next block's x-update.
+    The rows of send[p] are therefore ordered by the phase of the local end, the rows of recv[p] by the phase of
+    the remote end (= the peer's send order); both sides derive the same orders from (G, world, phases)."""
     edges, ptr, idx, ned, nend = graph_csr(G)
     V = G.number_of_nodes()
     nr = node_to_gpu(V, world)
+    phases = max(1, int(phases))
+    node_phase = {}
+    for r in range(world):
+        mine = [i for i in range(V) if nr[i] == r]
+        b = phase_bounds(len(mine), phases)
+        for li, g in enumerate(mine):
+            node_phase[g] = max(k for k in range(phases) if b[k] <= li)
     local_nodes = [i for i in range(V) if nr[i] == rank]
     sp = ShardPlan(world, rank, V, nr, local_nodes, {g: l for l, g in enumerate(local_nodes)}, edges, ptr, idx,
                    ned, nend)
@@ -72,27 +95,44 @@ def build_shard_plan(G, world: int, rank: int) -> ShardPlan:
         sp.local_edges.append(le)
     sp.peers = sorted(exch)
     sp.exch = {p: sorted(exch[p]) for p in sp.peers}
+    sp.phases, sp.node_phase = phases, node_phase
     for p in sp.peers:
+        mine = lambda e: int(edges[e][0]) if nr[int(edges[e][0])] == rank else int(edges[e][1])      # noqa: E731
+        theirs = lambda e: int(edges[e][1]) if nr[int(edges[e][0])] == rank else int(edges[e][0])    # noqa: E731
+        sorder = sorted(sp.exch[p], key=lambda e: (node_phase[mine(e)], e))
+        rorder = sorted(sp.exch[p], key=lambda e: (node_phase[theirs(e)], e))
         for k, e in enumerate(sp.exch[p]):
             sp.local_edges[sp.eslot[e]].xslot = k
+        for k, e in enumerate(sorder):
+            le = sp.local_edges[sp.eslot[e]]
+            le.sslot, le.sphase = k, node_phase[mine(e)]
+        for k, e in enumerate(rorder):
+            sp.local_edges[sp.eslot[e]].rslot = k
+        sp.send_rows[p] = [sum(1 for e in sorder if node_phase[mine(e)] < k) for k in range(phases + 1)]
+        sp.recv_rows[p] = [sum(1 for e in rorder if node_phase[theirs(e)] < k) for k in range(phases + 1)]
     return sp
 
 
-def post_exchange(dist, sp: ShardPlan, send: dict, recv: dict, group=None):
+def post_exchange(dist, sp: ShardPlan, send: dict, recv: dict, group=None, phase=None):
     """Post one neighbour exchange and return the requests: for every peer p, send[p] ([n_cut_p, n], this rank's
-    a = x + y of the cut edges shared with p, in `sp.exch[p]` order) goes to p and p's matching buffer lands in
-    recv[p].  Grouped P2P (ncclSend/ncclRecv inside one group on NCCL; works unchanged on gloo with CPU tensors)."""
+    a = x + y of the cut edges shared with p, row `LocalEdge.sslot`) goes to p and p's matching buffer lands in
+    recv[p] (row `LocalEdge.rslot`).  `phase=k` posts only the rows of exchange phase k (see build_shard_plan).
+    Grouped P2P (ncclSend/ncclRecv inside one group on NCCL; works unchanged on gloo with CPU tensors)."""
     if not sp.peers:
         return []
     ops = []
     for p in sp.peers:
-        ops.append(dist.P2POp(dist.isend, send[p], p, group=group))
-        ops.append(dist.P2POp(dist.irecv, recv[p], p, group=group))
-    return dist.batch_isend_irecv(ops)
+        s0, s1 = (0, len(sp.exch[p])) if phase is None else sp.send_rows[p][phase:phase + 2]
+        r0, r1 = (0, len(sp.exch[p])) if phase is None else sp.recv_rows[p][phase:phase + 2]
+        if s1 > s0:
+            ops.append(dist.P2POp(dist.isend, send[p][s0:s1], p, group=group))
+        if r1 > r0:
+            ops.append(dist.P2POp(dist.irecv, recv[p][r0:r1], p, group=group))
+    return dist.batch_isend_irecv(ops) if ops else []
 
 
 def exchange(dist, sp: ShardPlan, send: dict, recv: dict, group=None):
-    """Blocking form of post_exchange."""
+    """Blocking form of post_exchange (all phases at once)."""
     for req in post_exchange(dist, sp, send, recv, group):
         req.wait()
 

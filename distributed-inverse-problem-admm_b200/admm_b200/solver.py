@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _native as nat
 from .operators import Plan
-from .sharding import ShardPlan, build_shard_plan, post_exchange
+from .sharding import ShardPlan, build_shard_plan, phase_bounds, post_exchange
 
 
 def _torch():
@@ -39,7 +39,7 @@ class ADMMEngine:
     def __init__(self, thetas, sinograms, G, N, D=None, det_w=2.0, lam_tv=0.01, rho=1.0, Q=None, Wi_list=None,
                  node_prec=None, tv_mu=None, tv_sweeps=1, cg_iters=8, phantom_true=None, weighted_z=False,
                  device=0, dist=None, rank=0, world=1, group=None, node_group=None, fuse_pupdate=True,
-                 max_iters=200, ax_refresh_every=10, exchange="auto"):
+                 max_iters=200, ax_refresh_every=10, exchange="auto", exchange_phases=None):
         torch = _torch()
         nat.require_cuda()
         self.torch = torch
@@ -52,7 +52,15 @@ class ADMMEngine:
         self.S, self.C = int(tv_sweeps), int(cg_iters)
         self.dist, self.rank, self.world, self.group = dist, int(rank), int(world), group
         self._G = G
-        self.sp: ShardPlan = build_shard_plan(G, self.world, self.rank)
+        # NCCL exchange: posted in pieces, each right after the x-update of its block of nodes (hidden behind the next
+        # block's x-update).  Peer-memory exchange: nothing to post early -- the consumer reads the remote buffer.
+        # (measured on 2 and 8 B200s: splitting the x-updates into two blocks costs more in short-kernel tails than the
+        # earlier transfer hides, so the default is one phase -- profiles/README.md)
+        if exchange not in ("auto", "p2p", "push", "nccl"):
+            raise ValueError(f"unknown exchange mode {exchange!r}")
+        self.phases = 1 if (self.world == 1 or exchange != "nccl") else max(1, int(exchange_phases or 1))
+        self._peer_mem = exchange  # "p2p": consumers pull from the producer's buffer; "push": producers store into the consumer's
+        self.sp: ShardPlan = build_shard_plan(G, self.world, self.rank, self.phases)
         sp = self.sp
         self.Vg = sp.V
         self.loc = sp.local_nodes
@@ -198,9 +206,11 @@ class ADMMEngine:
         self._ncut = len(cut_sorted)
         self._peer_base, self._peer_slot, self._peer_ncut = {}, {}, {}
         self._ipc_mine, self._ipc_opened = None, []
-        if exchange == "nccl" or (exchange == "auto" and self.world > 2):
-            # measured on 8 B200s (profiles/README.md): pairwise send/recv lets rank pairs progress independently,
-            # while the peer-memory path needs a box-wide barrier whose wait adds to the per-rank imbalance
+        # measured on B200s (profiles/README.md): with 2 ranks the consumer-side pull wins (the remote reads ride inside
+        # the HBM-bound edge kernel); with 8 ranks the producer-side push on a side stream does (8.8 ms vs 9.0 NCCL,
+        # 9.2 pull per iteration of cfg4)
+        self._push = exchange == "push" or (exchange == "auto" and self.world > 2)
+        if exchange == "nccl":
             return "nccl"
         ok, handle = 1, b""
         try:
@@ -233,22 +243,36 @@ class ADMMEngine:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 1:
             self._bar = self.torch.zeros(1, dtype=self.torch.float32, device=self.dev)
+            self._side = None
+            import os
+            if self._push and os.environ.get("ADMM_B200_PUSH_SIDE", "1") == "1":
+                # the pack kernel IS the transfer (posted stores into the peers' buffers): it runs on a side stream, one
+                # block per SM, beside the HBM-bound TV pass and local-edge update
+                self._side = self.torch.cuda.Stream(device=self.dev)
+                nsm = self.torch.cuda.get_device_properties(self.dev).multi_processor_count
+                per_sm = int(os.environ.get("ADMM_B200_PUSH_BLOCKS_PER_SM", "2"))
+                nat.check(L.admm_plan_set(self.plan.handle, nat.OPT_PACK_BLOCKS, nsm * per_sm), "admm_plan_set")
             return "p2p"
-        if exchange == "p2p":
+        if exchange in ("p2p", "push"):
             raise RuntimeError("peer-memory exchange requested but CUDA IPC setup failed on some rank")
         return "nccl"
 
     def _remote_a(self, le, parity):
         """Device address (on THIS GPU's address space) of the remote end's a = x + y of cut edge `le`."""
         if self.exchange_mode == "p2p":
+            if self._push:     # the peer stored it into MY buffer
+                return self._ipc_mine + (parity * max(self._ncut, 1) + self._my_slot[le.e]) * self.n * 4
             p = le.peer
             return self._peer_base[p] + (parity * max(self._peer_ncut[p], 1) + self._peer_slot[p][le.e]) * self.n * 4
-        return self._addr(self.recv[le.peer], le.xslot)
+        return self._addr(self.recv[le.peer], le.rslot)
 
     def _pack_out(self, le, parity):
         if self.exchange_mode == "p2p":
+            if self._push:     # posted NVLink stores straight into the consumer's buffer
+                p = le.peer
+                return self._peer_base[p] + (parity * max(self._peer_ncut[p], 1) + self._peer_slot[p][le.e]) * self.n * 4
             return self._ipc_mine + (parity * max(self._ncut, 1) + self._my_slot[le.e]) * self.n * 4
-        return self._addr(self.send[le.peer], le.xslot)
+        return self._addr(self.send[le.peer], le.sslot)
 
     def _build_tables(self):
         torch, sp = self.torch, self.sp
@@ -293,7 +317,12 @@ class ADMMEngine:
             gj.append(le.gj)
             fl.append((1 if le.i_local else 0) | (2 if le.j_local else 0) | (4 if le.owns_dual else 0))
             if le.peer >= 0:
-                packs.append([xi, yi, self._pack_out(le, 0)] if le.i_local else [xj, yj, self._pack_out(le, 0)])
+                packs.append((le.sphase, [xi, yi, self._pack_out(le, 0)] if le.i_local else [xj, yj, self._pack_out(le, 0)],
+                              le))
+        packs.sort(key=lambda t: t[0])        # stable: phase-major, edge order inside a phase
+        self.pack_rows = [sum(1 for t in packs if t[0] < k) for k in range(self.phases + 1)]
+        pack_les = [t[2] for t in packs]
+        packs = [t[1] for t in packs]
         self.edge_desc = torch.tensor(ed if ed else [[0] * 11], dtype=torch.int64, device=self.dev)
         i32 = lambda a: torch.tensor(a if len(a) else [0], dtype=torch.int32, device=self.dev)  # noqa: E731
         self.edge_gi, self.edge_gj, self.edge_fl = i32(gi), i32(gj), i32(fl)
@@ -313,13 +342,12 @@ class ADMMEngine:
         if self.exchange_mode == "p2p":   # second parity of the double-buffered peer-memory exchange
             ed1 = self.edge_desc.clone()
             pk1 = self.pack_desc.clone()
-            k = 0
             for pos, le in enumerate(ordered):
                 if le.peer >= 0:
                     col = 5 if not le.i_local else 6           # admm_edge.ai / .aj
                     ed1[pos, col] = self._remote_a(le, 1)
-                    pk1[k, 2] = self._pack_out(le, 1)
-                    k += 1
+            for k, le in enumerate(pack_les):
+                pk1[k, 2] = self._pack_out(le, 1)
             self.edge_desc_par = [self.edge_desc, ed1]
             self.pack_desc_par = [self.pack_desc, pk1]
 
@@ -350,10 +378,19 @@ class ADMMEngine:
         st.reuse_ax = 0 if (self.k % self.ax_refresh_every == 0) else 1
         nat.check(L.admm_rhs0(h, sref, self.nbr_ptr.data_ptr(), self.nbr_z.data_ptr(), self.nbr_y.data_ptr(),
                               self.nbr_q.data_ptr(), 0, self.V, self._stream()), "admm_rhs0")
-        for n0 in range(0, self.V, self.node_group):
-            nn = min(self.node_group, self.V - n0)
-            nat.check(L.admm_x_update(h, sref, n0, nn, self.S, self.C, self._stream()), "admm_x_update")
+        reqs = []
+        bounds = phase_bounds(self.V, self.phases)
+        for ph in range(self.phases):
+            for n0 in range(bounds[ph], bounds[ph + 1], self.node_group):
+                nn = min(self.node_group, bounds[ph + 1] - n0)
+                nat.check(L.admm_x_update(h, sref, n0, nn, self.S, self.C, self._stream()), "admm_x_update")
+            if self.phases > 1:
+                if ph == self.phases - 1 and getattr(self, "time_exchange", False):
+                    self._ex_t0 = self.torch.cuda.Event(enable_timing=True)
+                    self._ex_t0.record()
+                reqs += self.exchange_start(ph)   # this block's x is final: its transfer hides behind the next block
         st.w_parity ^= ((self.S - (1 if st.defer_tv else 0)) & 1)
+        return reqs
 
     def tv_phase(self):
         """The deferred last TV pass (K3) of every local node."""
@@ -361,17 +398,30 @@ class ADMMEngine:
         nat.check(nat.lib().admm_tv_pass(self.plan.handle, ctypes.byref(st), 0, self.V, 1, self._stream()), "admm_tv_pass")
         st.w_parity ^= 1
 
-    def exchange_start(self):
-        """Pack a = x + y of this rank's cut-edge ends.  NCCL mode: post the grouped send/recv and return the requests.
-        Peer-memory mode: the pack kernel writes straight into the IPC-shared buffer the peers read from."""
-        if not self.n_pack:
+    def exchange_start(self, phase=None):
+        """Pack a = x + y of this rank's cut-edge ends (of exchange phase `phase`, or all).  NCCL mode: post the grouped
+        send/recv and return the requests.  Peer-memory mode: the pack kernel writes straight into the IPC-shared
+        buffer the peers read from."""
+        if self.world == 1:
             return []
         par = self.k & 1 if self.exchange_mode == "p2p" else 0
-        nat.check(nat.lib().admm_pack(self.plan.handle, self.pack_desc_par[par].data_ptr(), self.n_pack, self._stream()),
-                  "admm_pack")
+        k0, k1 = (0, self.n_pack) if phase is None else self.pack_rows[phase:phase + 2]
+        if self.exchange_mode == "p2p" and self._side is not None:
+            torch = self.torch
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)          # x is final
+            if k1 > k0:
+                nat.check(nat.lib().admm_pack(self.plan.handle, self.pack_desc_par[par].data_ptr() + k0 * 24, k1 - k0,
+                                              ctypes.c_void_p(self._side.cuda_stream)), "admm_pack")
+            self._pushed = torch.cuda.Event()
+            self._pushed.record(self._side)
+            return []
+        if k1 > k0:
+            nat.check(nat.lib().admm_pack(self.plan.handle, self.pack_desc_par[par].data_ptr() + k0 * 24, k1 - k0,
+                                          self._stream()), "admm_pack")
         if self.exchange_mode == "p2p":
             return []
-        return post_exchange(self.dist, self.sp, self.send, self.recv, self.group)
+        return post_exchange(self.dist, self.sp, self.send, self.recv, self.group, phase=phase)
 
     def edges_phase(self, reqs=()):
         """K5 on the local edges (overlaps the exchange), then on the cut edges, then the residual row."""
@@ -385,6 +435,8 @@ class ADMMEngine:
             nat.check(L.admm_edge_update(h, sref, desc.data_ptr(), nl, self.sums.data_ptr(), self._stream()),
                       "admm_edge_update")
         if self.exchange_mode == "p2p":
+            if self._side is not None:
+                self.torch.cuda.current_stream().wait_event(self._pushed)
             # device-side barrier: every rank's pack of this iteration has completed before anyone reads it; the
             # double buffer makes this the only synchronisation the exchange needs
             self.dist.all_reduce(self._bar, group=self.group)
@@ -409,17 +461,17 @@ class ADMMEngine:
             self.hist[self.k].copy_(self.row)
 
     def step(self):
-        self.nodes_phase()
-        reqs = ()
+        reqs = self.nodes_phase()
         if self.world > 1:
             timed = getattr(self, "time_exchange", False)
-            if timed:
-                ea, eb = (self.torch.cuda.Event(enable_timing=True) for _ in range(2))
-                ea.record()
-            reqs = self.exchange_start()      # x is final: the exchange runs under the TV pass and the local edges
+            if self.phases == 1:
+                if timed:
+                    self._ex_t0 = self.torch.cuda.Event(enable_timing=True)
+                    self._ex_t0.record()
+                reqs = self.exchange_start()  # x is final: the exchange runs under the TV pass and the local edges
             self.tv_phase()
             if timed:
-                self._edges_timed = (ea, eb)
+                self._edges_timed = (self._ex_t0, self.torch.cuda.Event(enable_timing=True))
         self.edges_phase(reqs)
         self.k += 1
 

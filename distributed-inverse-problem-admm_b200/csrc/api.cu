@@ -86,6 +86,7 @@ struct admm_plan {
     float* d_himg = nullptr;
     float* d_hsino = nullptr;
     int hsino_rows = 0;
+    int pack_blocks = 0;             // ADMM_OPT_PACK_BLOCKS (0: one block row per item)
 };
 
 extern "C" int admm_version(void) { return 100; }
@@ -138,13 +139,24 @@ extern "C" admm_plan* admm_plan_create(int N, int D, double det_w, int V, const 
     std::vector<int> optr(2 * (V + 1), 0), oidx(A > 0 ? A : 1, 0), anode(A > 0 ? A : 1, 0);
     double ext_f = 0.0, ext_b = 0.0;
     p->nTi = (N + FW - 1) / FW;
-    {   // segment length: as long as possible (fewer records) while the grid still fills the GPU several times
-        const long long want_blocks = 148LL * 6;
-        long long nseg = (want_blocks + (long long)V * p->nTi - 1) / ((long long)V * p->nTi);
-        const long long max_seg_count = (N + FL - 1) / FL;
-        nseg = std::max(1LL, std::min(nseg, max_seg_count));
-        int seg = (int)(((N + nseg - 1) / nseg + FL - 1) / FL) * FL;
-        p->seg = std::max(FL, std::min(seg, FSEG_MAX));
+    {   // segment length (a multiple of the slab length FL): long segments mean fewer records and less per-block
+        // setup, short ones a finer tail.  Model: time ~ waves(blocks) * (seg + c0) with 4 resident blocks per SM
+        // (__launch_bounds__(FTHREADS, 4)) and c0 ~ the per-block setup + record write-out in units of steps.
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const long long slots = 4LL * std::max(sms, 1);
+        const int c0 = 24;
+        long long best_cost = -1;
+        int best_seg = FL;
+        for (int seg = FL; seg <= FSEG_MAX; seg += FL) {
+            const long long nseg = (N + seg - 1) / seg;
+            const long long blocks = (long long)std::max(V, 1) * p->nTi * nseg;
+            const long long waves = (blocks + slots - 1) / slots;
+            const long long cost = waves * (std::min(seg, N) + c0);
+            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_seg = seg; }   // ties: the longer segment
+            if (seg >= N) break;
+        }
+        p->seg = best_seg;
     }
     const int Wm = std::min(FW, N), Km = std::min(p->seg, N);
     for (int a = 0; a < A; ++a) {
@@ -206,6 +218,17 @@ extern "C" void admm_plan_destroy(admm_plan* p) {
     cudaFree(p->d_ang); cudaFree(p->d_optr); cudaFree(p->d_oidx); cudaFree(p->d_aptr); cudaFree(p->d_anode);
     cudaFree(p->d_recs); cudaFree(p->d_jstart); cudaFree(p->d_himg); cudaFree(p->d_hsino);
     delete p;
+}
+
+extern "C" int admm_plan_set(admm_plan* p, int what, long long value) {
+    if (!p) return fail(ADMM_ERR_ARG, "admm_plan_set: null plan");
+    switch (what) {
+        case ADMM_OPT_PACK_BLOCKS:
+            if (value < 0 || value > 65535) return fail(ADMM_ERR_ARG, "admm_plan_set: pack blocks out of range");
+            p->pack_blocks = (int)value;
+            return ADMM_OK;
+        default: return fail(ADMM_ERR_ARG, "admm_plan_set: unknown option");
+    }
 }
 
 extern "C" long long admm_plan_info(const admm_plan* p, int what) {
@@ -475,8 +498,8 @@ extern "C" int admm_edge_update(admm_plan* p, const admm_state* s, const admm_ed
 extern "C" int admm_pack(admm_plan* p, const admm_pack_item* d_items, int nitems, void* stream) {
     if (!p) return fail(ADMM_ERR_ARG, "admm_pack: null plan");
     PackParams K{};
-    K.items = reinterpret_cast<const PackDesc*>(d_items); K.n = (long long)p->N * p->N;
-    CK(launch_pack(K, nitems, (cudaStream_t)stream));
+    K.items = reinterpret_cast<const PackDesc*>(d_items); K.n = (long long)p->N * p->N; K.nitems = nitems;
+    CK(launch_pack(K, nitems, p->pack_blocks, (cudaStream_t)stream));
     return ADMM_OK;
 }
 

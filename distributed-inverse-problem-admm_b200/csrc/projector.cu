@@ -325,7 +325,7 @@ fwd_reduce_kernel(const FwdReduceParams P) {
 // K2 back-projection: exact transpose of K1 as an atomics-free gather:
 //   (A^T q)[ix,iy] = sum_theta (h/|a|) sum_j max(0, 1 - |tau - j|/omega) q[theta, j]
 // One block owns a BTX x BTY pixel tile, stages every angle's detector window (pre-scaled by the step
-// weight and the node precision) into shared memory and accumulates in registers (4 pixels / thread).
+// weight and the node precision) into shared memory and accumulates in registers (4*BPG pixels / thread).
 // Epilogues fuse the rest of the CG operator:  H v = A^T P A v + rhoD .* v + mu K^T K v, the <v, Hv>
 // / <r, r> block reductions (warp shuffle + last-block-done grid reduce), and the CG initial residual.
 // =================================================================================================
@@ -344,13 +344,15 @@ back_tile_kernel(const BackParams P) {
     const int N = P.N, D = P.D, bspan = P.bspan;
     const int X0 = blockIdx.y * BTX, Y0 = blockIdx.x * BTY;
     const int tid = threadIdx.x;
-    const int lx = tid >> 3, ly = (tid & 7) * 4;          // pixels (X0+lx, Y0+ly+{0..3}) and (.., Y0+32+ly+{0..3})
+    const int lx = tid >> 3, ly = (tid & 7) * 4;          // pixels (X0+lx, Y0+32*g+ly+{0..3}), g < BPG
     const int ix = X0 + lx;
     const int abeg = P.aptr[node], aend = P.aptr[node + 1];
     const double cx = 0.5 * (N - 1), cj = 0.5 * (D - 1);
     const float prec = (MODE == BACK_COLNORM2 || P.prec == nullptr) ? 1.f : P.prec[node];
 
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float acc[4 * BPG];
+#pragma unroll
+    for (int px = 0; px < 4 * BPG; ++px) acc[px] = 0.f;
     float fx = (float)lx, fy = (float)ly;
     opaque(fx);
     opaque(fy);
@@ -393,7 +395,7 @@ back_tile_kernel(const BackParams P) {
                 const float c1 = fmaf(-0.5f, a, 1.f);
                 const unsigned qa = s_qa[ai];
 #pragma unroll
-                for (int px = 0; px < 8; ++px) {
+                for (int px = 0; px < 4 * BPG; ++px) {
                     const float off = (float)((px & 3) + 32 * (px >> 2));
                     const float v = (px == 0) ? tb : fmaf(off, c.z, tb);
                     const float fi = v + kMagic;
@@ -409,7 +411,7 @@ back_tile_kernel(const BackParams P) {
                 const float* __restrict__ qa = qs + ai * bspan;
                 const float om = 1.f / a;
 #pragma unroll
-                for (int px = 0; px < 8; ++px) {
+                for (int px = 0; px < 4 * BPG; ++px) {
                     const float off = (float)((px & 3) + 32 * (px >> 2));
                     const float tau = fmaf(off, c.z, tb) + 0.5f;
                     const int jlo = (int)ceilf(tau - om), jhi = (int)floorf(tau + om);
@@ -431,7 +433,7 @@ back_tile_kernel(const BackParams P) {
     if (MODE == BACK_PLAIN || MODE == BACK_COLNORM2) {
         if (rowok) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < BPG; ++h) {
                 const int iy = Y0 + ly + 32 * h;
                 float* o = P.out + nb + (long long)ix * N + iy;
                 if (iy + 3 < N && vecok) st4(o, make_float4(acc[4 * h], acc[4 * h + 1], acc[4 * h + 2], acc[4 * h + 3]));
@@ -445,7 +447,7 @@ back_tile_kernel(const BackParams P) {
         // tiles that touch no image border take the unguarded path
         const bool interior = vecok && X0 >= 1 && X0 + BTX < N && Y0 >= 1 && Y0 + BTY < N;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < BPG; ++h) {
             const int iy = Y0 + ly + 32 * h;
             const long long g = (long long)ix * N + iy;
             float res[4];

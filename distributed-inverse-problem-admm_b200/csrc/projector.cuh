@@ -54,8 +54,9 @@ struct FwdReduceParams {
 
 // ---- K2 back-projection (gather) with fused epilogues ---------------------------------------------
 constexpr int BTX = 32;        // tile rows (ix)
-constexpr int BTY = 64;        // tile cols (iy)
-constexpr int BTHREADS = 256;  // 8 pixels per thread: two float4 groups 32 columns apart
+constexpr int BPG = 4;         // float4 pixel groups per thread (32 columns apart)
+constexpr int BTY = 32 * BPG;  // tile cols (iy)
+constexpr int BTHREADS = 256;  // 4*BPG pixels per thread
 constexpr int BAC = 16;        // angles staged per chunk
 
 enum BackMode : int {

@@ -423,17 +423,23 @@ edge_kernel(const EdgeParams P) {
 // a = x + y for the cut-edge ends this rank sends
 __global__ void __launch_bounds__(256)
 pack_kernel(const PackParams P) {
-    const PackDesc d = P.items[blockIdx.y];
-    const float* __restrict__ x = reinterpret_cast<const float*>(d.x);
-    const float* __restrict__ y = reinterpret_cast<const float*>(d.y);
-    float* __restrict__ o = reinterpret_cast<float*>(d.out);
-    const long long n4 = ((P.n & 3) == 0) ? (P.n >> 2) : 0;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x) {
-        const float4 a = ld4(x + 4 * k), b = ld4(y + 4 * k);
-        st4(o + 4 * k, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w));
+    // grid.y == nitems: one item per block row; grid.y == 1 (narrow launch, `out` in a peer's memory): every block
+    // walks all items, so a few resident blocks keep the NVLink stores in flight next to the HBM-bound kernels
+    for (int it = blockIdx.y; it < P.nitems; it += gridDim.y) {
+        const PackDesc d = P.items[it];
+        const float* __restrict__ x = reinterpret_cast<const float*>(d.x);
+        const float* __restrict__ y = reinterpret_cast<const float*>(d.y);
+        float* __restrict__ o = reinterpret_cast<float*>(d.out);
+        const long long n4 = ((P.n & 3) == 0) ? (P.n >> 2) : 0;
+        const long long step = (long long)gridDim.x * blockDim.x;
+#pragma unroll 4
+        for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += step) {
+            const float4 a = ld4(x + 4 * k), b = ld4(y + 4 * k);
+            st4(o + 4 * k, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w));
+        }
+        for (long long k = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += step)
+            o[k] = x[k] + y[k];
     }
-    for (long long k = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += (long long)gridDim.x * blockDim.x)
-        o[k] = x[k] + y[k];
 }
 
 // Per-iteration bookkeeping (block_6_admm_loop_ver2.py:232-264): fold the per-edge sums (in G.edges()
@@ -531,9 +537,10 @@ cudaError_t launch_edges(const EdgeParams& P, int nedges, int nblk, cudaStream_t
     { ProfScope ps(KC_EDGE, st); edge_kernel<<<dim3(nblk, nedges), 256, 0, st>>>(P); }
     return cudaGetLastError();
 }
-cudaError_t launch_pack(const PackParams& P, int nitems, cudaStream_t st) {
+cudaError_t launch_pack(const PackParams& P, int nitems, int narrow_blocks, cudaStream_t st) {
     if (nitems <= 0) return cudaSuccess;
-    { ProfScope ps(KC_PACK, st); pack_kernel<<<dim3(stream_blocks(P.n, 4), nitems), 256, 0, st>>>(P); }
+    const dim3 grid = narrow_blocks > 0 ? dim3(narrow_blocks, 1) : dim3(stream_blocks(P.n, 4), nitems);
+    { ProfScope ps(KC_PACK, st); pack_kernel<<<grid, 256, 0, st>>>(P); }
     return cudaGetLastError();
 }
 cudaError_t launch_finalize(const FinalizeParams& P, cudaStream_t st) {

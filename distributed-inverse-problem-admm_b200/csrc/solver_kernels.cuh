@@ -61,7 +61,7 @@ struct EdgeParams {
 };
 
 struct PackDesc { unsigned long long x, y, out; };
-struct PackParams { const PackDesc* items; long long n; };
+struct PackParams { const PackDesc* items; long long n; int nitems; };
 
 struct FinalizeParams {
     const double* sums;       // [E][5]
@@ -87,7 +87,7 @@ cudaError_t launch_sino_axpy(const SinoParams& P, cudaStream_t st);
 cudaError_t launch_sino_resid(const SinoParams& P, int nodes, cudaStream_t st);
 cudaError_t launch_rhs0(const RhsParams& P, int nodes, cudaStream_t st);
 cudaError_t launch_edges(const EdgeParams& P, int nedges, int nblk, cudaStream_t st);
-cudaError_t launch_pack(const PackParams& P, int nitems, cudaStream_t st);
+cudaError_t launch_pack(const PackParams& P, int nitems, int narrow_blocks, cudaStream_t st);
 cudaError_t launch_finalize(const FinalizeParams& P, cudaStream_t st);
 
 }  // namespace admm

@@ -105,6 +105,11 @@ void admm_plan_destroy(admm_plan* plan);
 #define ADMM_INFO_BACK_SPAN 7
 #define ADMM_INFO_WS_BYTES 8
 long long admm_plan_info(const admm_plan* plan, int what);
+/* Tunables.  ADMM_OPT_PACK_BLOCKS = B > 0: admm_pack runs as B blocks that walk all items (for `out` pointers in a
+ * peer GPU's memory: a narrow grid keeps NVLink stores in flight beside HBM-bound kernels on another stream);
+ * 0 (default): one block row per item. */
+#define ADMM_OPT_PACK_BLOCKS 0
+int admm_plan_set(admm_plan* plan, int what, long long value);
 
 /* ---- K1 / K2 / K2b: the operator  (device pointers) ---------------------------------------------------
  * admm_forward  : `Ai @ x` / op(x)            block_6_admm_loop_ver2.py:145,193; block_2_load_odl_data.py:149

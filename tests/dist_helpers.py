@@ -9,14 +9,15 @@ import numpy as np
 def run_rank(rank, world, port, cfg, ret):
     import torch
     import torch.distributed as dist
-    from admm_b200.sharding import build_shard_plan, exchange
+    from admm_b200.sharding import build_shard_plan, phase_bounds, post_exchange
     from oracle import oracle as O
     dist.init_process_group("gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
     try:
         N, M, V, iters, rho, lam = cfg["N"], cfg["M"], cfg["V"], cfg["iters"], cfg["rho"], cfg["lam"]
         n = N * N
         G = O.make_graph(cfg["graph"], V, seed=0, p=0.4, degree=3)
-        sp = build_shard_plan(G, world, rank)
+        phases = cfg.get("phases", 1)
+        sp = build_shard_plan(G, world, rank, phases)
         thetas = O.node_angles(M, V)
         img = O.shepp_logan(N)
         ops = {g: O.JosephOperator(N, thetas[g]) for g in sp.local_nodes}
@@ -33,23 +34,29 @@ def run_rank(rank, world, port, cfg, ret):
         recv = {p: torch.zeros(len(sp.exch[p]), n, dtype=torch.float64) for p in sp.peers}
         pri_hist, dual_hist = [], []
         for _ in range(iters):
-            for g in sp.local_nodes:
+            reqs = []
+            bounds = phase_bounds(len(sp.local_nodes), phases)
+            for li, g in enumerate(sp.local_nodes):
                 cons = np.zeros(n)
                 for kk in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1]):
                     s, end = sp.eslot[int(sp.nbr_edge[kk])], int(sp.nbr_end[kk])
                     cons += rho * (z[s] - y[s][end])
                 deg = int(sp.nbr_ptr[g + 1] - sp.nbr_ptr[g])
                 O.x_update(ops[g], 1.0, atb[g] + cons, rho * deg, rho, lam, 1, 6, x[g], d[g], w[g])
-            for le in sp.local_edges:                       # pack a = x + y of this rank's end of every cut edge
-                if le.peer >= 0:
-                    g, end = (le.gi, 0) if le.i_local else (le.gj, 1)
-                    send[le.peer][le.xslot] = torch.from_numpy(x[g] + y[le.slot][end])
-            exchange(dist, sp, send, recv)
+                if li + 1 in bounds[1:]:                    # a phase just finished: pack its cut-edge ends and post them
+                    for ph in [k for k in range(phases) if bounds[k + 1] == li + 1]:
+                        for le in sp.local_edges:           # a = x + y of this rank's end of every cut edge of the phase
+                            if le.peer >= 0 and le.sphase == ph:
+                                gg, end = (le.gi, 0) if le.i_local else (le.gj, 1)
+                                send[le.peer][le.sslot] = torch.from_numpy(x[gg] + y[le.slot][end])
+                        reqs += post_exchange(dist, sp, send, recv, phase=ph if phases > 1 else None)
+            for r in reqs:
+                r.wait()
             row = np.zeros(2 + 2 * V)
             for le in sp.local_edges:
                 s = le.slot
-                ai = x[le.gi] + y[s][0] if le.i_local else recv[le.peer][le.xslot].numpy()
-                aj = x[le.gj] + y[s][1] if le.j_local else recv[le.peer][le.xslot].numpy()
+                ai = x[le.gi] + y[s][0] if le.i_local else recv[le.peer][le.rslot].numpy()
+                aj = x[le.gj] + y[s][1] if le.j_local else recv[le.peer][le.rslot].numpy()
                 zn = (ai + aj) / 2.0
                 if le.i_local:
                     ri = x[le.gi] - zn

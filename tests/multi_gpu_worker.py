@@ -37,6 +37,10 @@ def main():
                   cg_iters=6, weighted_z=wq)
         xs, hs = decentralized_admm(ops, sinos, G, Wl, Q, N, exchange="p2p", **kw)       # peer memory over NVLink
         xn, hn = decentralized_admm(ops, sinos, G, Wl, Q, N, exchange="nccl", **kw)      # grouped send/recv
+        xp, hp = decentralized_admm(ops, sinos, G, Wl, Q, N, exchange="push", **kw)      # producers store into the peers
+        x2, h2 = decentralized_admm(ops, sinos, G, Wl, Q, N, exchange="nccl", exchange_phases=2, **kw)
+        assert all(np.array_equal(a, b) for a, b in zip(xs, xp)) and hs["primal"] == hp["primal"]
+        assert all(np.array_equal(a, b) for a, b in zip(xs, x2)) and hs["primal"] == h2["primal"]
         x1, h1 = decentralized_admm(ops, sinos, G, Wl, Q, N, distributed=False, **kw)
         assert all(np.array_equal(a, b) for a, b in zip(xs, xn)) and hs["primal"] == hn["primal"]
         cut = cut_statistics(G, world)["cut"]

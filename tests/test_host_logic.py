@@ -193,3 +193,23 @@ def test_boundary_accepts_every_call_the_reference_makes():
     src = open(os.path.join(ROOT, "distributed-inverse-problem-admm_b200", "block_2_load_odl_data.py")).read()
     for key in facts["data_keys"]:
         assert f'"{key}"' in src, key
+
+
+def test_phased_exchange_orders_match_on_both_sides():
+    """send rows of rank a -> p are the recv rows of p <- a, phase by phase, for every pair (8 ranks, 64-node ER)."""
+    from admm_b200.sharding import build_shard_plan, phase_bounds
+    from oracle import oracle as O
+    assert phase_bounds(8, 2) == [0, 4, 8] and phase_bounds(7, 2) == [0, 4, 7] and phase_bounds(1, 2) == [0, 1, 1]
+    G = O.make_graph("er", 64, seed=0, p=0.1)
+    for phases in (1, 2, 3):
+        sps = [build_shard_plan(G, 8, r, phases) for r in range(8)]
+        for a in range(8):
+            assert sorted(sps[a].node_phase) == list(range(64))
+            for p in sps[a].peers:
+                assert sps[a].send_rows[p] == sps[p].recv_rows[a]
+                assert sps[a].send_rows[p][-1] == len(sps[a].exch[p])
+                sa = {le.sslot: (le.e, le.sphase) for le in sps[a].local_edges if le.peer == p}
+                rb = {le.rslot: le.e for le in sps[p].local_edges if le.peer == a}
+                assert {k: v[0] for k, v in sa.items()} == rb
+                for k, (e, ph) in sa.items():
+                    assert sps[a].send_rows[p][ph] <= k < sps[a].send_rows[p][ph + 1]
