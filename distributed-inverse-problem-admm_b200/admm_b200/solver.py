@@ -319,7 +319,9 @@ class ADMMEngine:
             if le.peer >= 0:
                 packs.append((le.sphase, [xi, yi, self._pack_out(le, 0)] if le.i_local else [xj, yj, self._pack_out(le, 0)],
                               le))
-        packs.sort(key=lambda t: t[0])        # stable: phase-major, edge order inside a phase
+        # phase-major; inside a phase rank r serves peer r+1 first, then r+2, ... so that at any moment every GPU is the
+        # destination of one producer (the narrow push kernel walks the items in this order)
+        packs.sort(key=lambda t: (t[0], (t[2].peer - self.rank) % self.world))
         self.pack_rows = [sum(1 for t in packs if t[0] < k) for k in range(self.phases + 1)]
         pack_les = [t[2] for t in packs]
         packs = [t[1] for t in packs]
