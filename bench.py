@@ -266,7 +266,8 @@ def run_reference(args, cfg, rank):
 def workload_config(args, cfg, G):
     c = {"workload": f"{args.config}: {cfg['desc']}", "N": cfg["N"], "angles": cfg["M"], "nodes": total_nodes(cfg),
          "graph": cfg["graph"], "lam_tv": LAM, "rho": RHO, "tv_mu": RHO, "tv_sweeps": args.tv_sweeps,
-         "cg_iters": args.cg_iters, "noise_sigma": SIGMA, "partition": "contiguous",
+         "cg_iters": args.cg_iters, "noise_sigma": SIGMA,
+         "partition": "single GPU" if args.gpus == 1 else getattr(args, "partition_used", args.partition),
          "inputs_larger_than_L2": True, "stop_test": "disabled in the timed region"}
     if args.gpus > 1:
         c["parallelism"] = f"graph nodes sharded over {args.gpus} GPUs, cut-edge exchange={getattr(args, 'exchange_used', args.exchange)}" + (f" in {args.phases_used} phases" if getattr(args, "phases_used", 1) > 1 else "")
@@ -288,6 +289,8 @@ def main():
     ap.add_argument("--slices", type=int, default=0, help="override the slice count of cfg5")
     ap.add_argument("--no-fuse", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "push", "nccl"])
+    ap.add_argument("--partition", default="auto", choices=["auto", "mincut", "contiguous"],
+                    help="node -> GPU map when sharded (auto: balanced min-cut for <= 256 nodes)")
     ap.add_argument("--exchange-phases", type=int, default=None,
                     help="NCCL exchange: post the cut-edge transfers in this many pieces per iteration (default 2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -328,10 +331,15 @@ def main():
     eng = ADMMEngine(thetas, sinos, G, cfg["N"], lam_tv=LAM, rho=RHO, Q=Q, Wi_list=Wl, node_prec=node_prec(cfg),
                      tv_sweeps=S, cg_iters=C, phantom_true=img, device=local, dist=dist if world > 1 else None,
                      rank=rank, world=world, node_group=args.node_group or None, fuse_pupdate=not args.no_fuse,
-                     max_iters=total, exchange=args.exchange, exchange_phases=args.exchange_phases)
+                     max_iters=total, exchange=args.exchange, exchange_phases=args.exchange_phases, partition=args.partition)
 
     args.exchange_used = "push" if (eng.exchange_mode == "p2p" and getattr(eng, "_push", False)) else eng.exchange_mode
     args.phases_used = eng.phases
+    if world > 1:
+        from admm_b200.sharding import cut_statistics
+        cs = cut_statistics(G, world, eng.node_rank)
+        contiguous = eng.node_rank == [(i * world) // len(eng.node_rank) for i in range(len(eng.node_rank))]
+        args.partition_used = ("contiguous" if contiguous else "balanced min-cut") + f" ({cs['cut']} of {cs['edges']} edges cut, max {max(cs['per_rank_ends'])} ends on a rank)"
 
     def barrier():
         if world > 1:
@@ -466,7 +474,7 @@ def main():
                                           cg_iters=C, tv_sweeps=S, node_prec=node_prec(cfg), device=local,
                                           node_group=args.node_group or None, fuse_pupdate=not args.no_fuse,
                                           return_engine=True, exchange=args.exchange, gather="rank0",
-                                          exchange_phases=args.exchange_phases)
+                                          exchange_phases=args.exchange_phases, partition=args.partition)
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:

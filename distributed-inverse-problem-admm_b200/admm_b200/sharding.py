@@ -1,6 +1,6 @@
 """Node sharding of the consensus graph over the GPUs of one box -- pure host logic, bit-exact.
 
-Units = graph nodes.  gpu(i) = (i*G)//V (contiguous blocks).  Edge (i, j), i < j, is *local* to a rank that owns
+Units = graph nodes.  gpu(i) = (i*G)//V (contiguous blocks) or a balanced min-cut map (partition_nodes).  Edge (i, j), i < j, is *local* to a rank that owns
 both ends and *cut* otherwise; a cut edge lives on both owners: each keeps a replica of z_ij and its own
 y_ij,end, receives the peer's a = x + y once per iteration (NCCL send/recv) and computes the identical z' (the
 midpoint / W-weighted fusions are symmetric in (i, j)).  The owner of the min end contributes the edge's dual
@@ -58,19 +58,85 @@ class ShardPlan:
         return sum(len(v) for v in self.exch.values())
 
 
+def _map_score(edges, nr, world):
+    """(largest number of cut-edge ends on one rank, cut edges): the slowest rank's exchange volume comes first."""
+    per = [0] * world
+    cut = 0
+    for i, j in edges:
+        a, b = nr[int(i)], nr[int(j)]
+        if a != b:
+            per[a] += 1
+            per[b] += 1
+            cut += 1
+    return (max(per) if per else 0, cut)
+
+
+def partition_nodes(G, world: int, method: str = "auto", trials: int = 16, seed: int = 1234) -> list:
+    """Node -> GPU map with V//world or V//world+1 nodes per rank (the x-update work is per node, so the map stays
+    balanced).  "contiguous": gpu(i) = (i*G)//V (SURVEY 8(e)).  "mincut": deterministic multi-start pairwise-swap
+    refinement (Kernighan-Lin moves on the cut size, vectorised: gain(i,j) = P[i,part j] + P[j,part i] - 2 A[i,j]
+    with P[i,w] = #nbrs of i in w - #nbrs of i in its own part), best of `trials` starts by (max cut-edge ends on a
+    rank, cut edges); never worse than contiguous, which is start 0.  "auto": mincut for V <= 256, else contiguous
+    (the search is O(V^2) per move; slice-batched graphs are disjoint unions that the contiguous map already keeps
+    whole).  Every rank calls this with the same arguments and gets the same list."""
+    V = G.number_of_nodes()
+    cont = node_to_gpu(V, world)
+    if method not in ("auto", "mincut", "contiguous"):
+        raise ValueError(f"unknown partition method {method!r}")
+    if world <= 1 or method == "contiguous" or (method == "auto" and V > 256) or V <= world:
+        return cont
+    edges = graph_csr(G)[0]
+    if len(edges) == 0:
+        return cont
+    A = np.zeros((V, V), dtype=np.int32)
+    for i, j in edges:
+        A[int(i), int(j)] = A[int(j), int(i)] = 1
+    rng = np.random.RandomState(seed)
+    best, best_score = cont, _map_score(edges, cont, world)
+    rows = np.arange(V)
+    for t in range(max(1, trials)):
+        part = np.asarray(cont, dtype=np.int64)
+        if t > 0:
+            part = part[rng.permutation(V)]
+        for _ in range(8 * V):
+            X = np.zeros((V, world), dtype=np.int32)
+            X[rows, part] = 1
+            C = A @ X                                   # C[i, w]: neighbours of i in part w
+            P = C - C[rows, part][:, None]
+            M = P[:, part]                              # M[i, j] = P[i, part(j)]
+            gain = M + M.T - 2 * A
+            gain[part[:, None] == part[None, :]] = -1
+            k = int(np.argmax(gain))
+            i, j = divmod(k, V)
+            if gain[i, j] <= 0:
+                break
+            part[i], part[j] = part[j], part[i]
+        # canonical labels: ranks in order of their smallest node id (keeps rank 0 holding node 0, deterministic)
+        order = {}
+        for g in range(V):
+            order.setdefault(int(part[g]), len(order))
+        cand = [order[int(part[g])] for g in range(V)]
+        sc = _map_score(edges, cand, world)
+        if sc < best_score:
+            best, best_score = cand, sc
+    return best
+
+
 def phase_bounds(count: int, phases: int) -> list:
     """Local-node index ranges of the x-update phases: phase k = [b[k], b[k+1]) (contiguous, sizes differ by <= 1)."""
     return [-((-k * count) // phases) for k in range(phases)] + [count]
 
 
-def build_shard_plan(G, world: int, rank: int, phases: int = 1) -> ShardPlan:
+def build_shard_plan(G, world: int, rank: int, phases: int = 1, node_rank=None) -> ShardPlan:
     """phases > 1: every rank runs its x-updates in `phases` contiguous node blocks and posts the a = x + y of a
     block's cut-edge ends as soon as the block is done, so the transfer hides behind the next block's x-update.
     The rows of send[p] are therefore ordered by the phase of the local end, the rows of recv[p] by the phase of
     the remote end (= the peer's send order); both sides derive the same orders from (G, world, phases)."""
     edges, ptr, idx, ned, nend = graph_csr(G)
     V = G.number_of_nodes()
-    nr = node_to_gpu(V, world)
+    nr = node_to_gpu(V, world) if node_rank is None else [int(r) for r in node_rank]
+    if len(nr) != V or any(r < 0 or r >= world for r in nr):
+        raise ValueError("node_rank must give a rank in [0, world) for every node")
     phases = max(1, int(phases))
     node_phase = {}
     for r in range(world):
@@ -137,10 +203,10 @@ def exchange(dist, sp: ShardPlan, send: dict, recv: dict, group=None):
         req.wait()
 
 
-def cut_statistics(G, world: int) -> dict:
-    """Edges cut by the contiguous map and the per-rank exchange volume in units of n floats."""
+def cut_statistics(G, world: int, node_rank=None) -> dict:
+    """Edges cut by the node map (default: contiguous) and the per-rank exchange volume in units of n floats."""
     edges = graph_csr(G)[0]
-    nr = node_to_gpu(G.number_of_nodes(), world)
+    nr = node_to_gpu(G.number_of_nodes(), world) if node_rank is None else list(node_rank)
     cut = [(int(i), int(j)) for i, j in edges if nr[int(i)] != nr[int(j)]]
     per_rank = [0] * world
     for i, j in cut:

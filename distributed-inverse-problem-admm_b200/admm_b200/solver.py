@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _native as nat
 from .operators import Plan
-from .sharding import ShardPlan, build_shard_plan, phase_bounds, post_exchange
+from .sharding import ShardPlan, build_shard_plan, partition_nodes, phase_bounds, post_exchange
 
 
 def _torch():
@@ -39,7 +39,7 @@ class ADMMEngine:
     def __init__(self, thetas, sinograms, G, N, D=None, det_w=2.0, lam_tv=0.01, rho=1.0, Q=None, Wi_list=None,
                  node_prec=None, tv_mu=None, tv_sweeps=1, cg_iters=8, phantom_true=None, weighted_z=False,
                  device=0, dist=None, rank=0, world=1, group=None, node_group=None, fuse_pupdate=True,
-                 max_iters=200, ax_refresh_every=10, exchange="auto", exchange_phases=None):
+                 max_iters=200, ax_refresh_every=10, exchange="auto", exchange_phases=None, partition="auto"):
         torch = _torch()
         nat.require_cuda()
         self.torch = torch
@@ -60,7 +60,10 @@ class ADMMEngine:
             raise ValueError(f"unknown exchange mode {exchange!r}")
         self.phases = 1 if (self.world == 1 or exchange != "nccl") else max(1, int(exchange_phases or 1))
         self._peer_mem = exchange  # "p2p": consumers pull from the producer's buffer; "push": producers store into the consumer's
-        self.sp: ShardPlan = build_shard_plan(G, self.world, self.rank, self.phases)
+        # node -> GPU map: balanced min-cut by default (every rank computes the same map), "contiguous", or a list
+        self.node_rank = (partition_nodes(G, self.world, partition) if isinstance(partition, str)
+                          else [int(r) for r in partition])
+        self.sp: ShardPlan = build_shard_plan(G, self.world, self.rank, self.phases, self.node_rank)
         sp = self.sp
         self.Vg = sp.V
         self.loc = sp.local_nodes
@@ -206,10 +209,9 @@ class ADMMEngine:
         self._ncut = len(cut_sorted)
         self._peer_base, self._peer_slot, self._peer_ncut = {}, {}, {}
         self._ipc_mine, self._ipc_opened = None, []
-        # measured on B200s (profiles/README.md): with 2 ranks the consumer-side pull wins (the remote reads ride inside
-        # the HBM-bound edge kernel); with 8 ranks the producer-side push on a side stream does (8.8 ms vs 9.0 NCCL,
-        # 9.2 pull per iteration of cfg4)
-        self._push = exchange == "push" or (exchange == "auto" and self.world > 2)
+        # measured on B200s (profiles/README.md): the producer-side push on a side stream wins at every rank count once
+        # the node map is the balanced min-cut one (2 GPUs: 22.6 vs 22.9 ms pull; 8 GPUs: 8.35 vs 9.0 NCCL, 9.2 pull)
+        self._push = exchange in ("push", "auto")
         if exchange == "nccl":
             return "nccl"
         ok, handle = 1, b""
@@ -233,7 +235,7 @@ class ADMMEngine:
                     self._peer_base[p] = ptr.value
                     self._ipc_opened.append(ptr.value)
                     self._peer_ncut[p] = infos[p][2]
-                    sp_p = build_shard_plan(self._G, self.world, p)
+                    sp_p = build_shard_plan(self._G, self.world, p, 1, self.node_rank)
                     self._peer_slot[p] = {e: k for k, e in enumerate(sorted(le.e for le in sp_p.local_edges if le.peer >= 0))}
             except Exception:
                 ok = 0
@@ -549,16 +551,19 @@ class ADMMEngine:
             host[lo:lo + self.V].copy_(gathered[lo:lo + self.V], non_blocking=True)
             torch.cuda.synchronize(self.dev)
             arr = host.numpy()
-            out = []
-            for k in range(self.world):
-                out.extend((arr[k * mx + i] if k == self.rank else None) for i in range(counts[k]))
+            out = [None] * self.Vg
+            for li, g in enumerate(self.loc):
+                out[g] = arr[lo + li]
             return out
         host.copy_(gathered, non_blocking=True)
         torch.cuda.synchronize(self.dev)
         arr = host.numpy()
-        out = []
-        for k in range(self.world):
-            out.extend(arr[k * mx + i] for i in range(counts[k]))
+        out = [None] * self.Vg
+        seen = [0] * self.world
+        for g in range(self.Vg):          # rank k's rows are its nodes in ascending global id
+            k = self.sp.node_rank[g]
+            out[g] = arr[k * mx + seen[k]]
+            seen[k] += 1
         return out
 
     def close(self):

@@ -48,7 +48,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                        # --- B200 solver controls (not in the reference) ---
                        cg_iters=8, tv_sweeps=1, tv_mu=None, node_prec=None, weighted_z=False, scs_eps=None,
                        check_every=1, node_group=None, fuse_pupdate=True, device=None, return_engine=False,
-                       distributed=None, ax_refresh_every=10, exchange="auto", gather="all", exchange_phases=None,
+                       distributed=None, ax_refresh_every=10, exchange="auto", gather="all", exchange_phases=None, partition="auto",
                        **kwargs):
     """Returns x_per_node as list of reconstructions, each length n, and the history of residual norms
     (block_6_admm_loop_ver2.py:21-24).
@@ -60,7 +60,8 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
     (`distributed=False` keeps the whole graph on this rank's GPU).  `exchange`: "p2p" reads the cut-edge iterates
     straight from the peers' memory over NVLink inside the edge kernel (CUDA IPC), "push" stores them into the
     peers' memory from the pack kernel on a side stream, "nccl" uses grouped send/recv (optionally posted in
-    `exchange_phases` pieces as node blocks finish), "auto" picks by rank count (2 ranks: p2p, more: push).  `gather`: "all" (every rank returns every node's x, like the single-process
+    `exchange_phases` pieces as node blocks finish), "auto" = push.  `partition`: node -> GPU map, "auto" (balanced min-cut
+    for V <= 256), "mincut", "contiguous" ((i*G)//V) or an explicit list of ranks.  `gather`: "all" (every rank returns every node's x, like the single-process
     reference) or "rank0" (only rank 0 receives the full list; the others get their own nodes and None elsewhere).
     """
     for k in list(kwargs):
@@ -98,7 +99,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                      cg_iters=min(int(cg_iters), int(max_inner_iters)), phantom_true=phantom_true,
                      weighted_z=weighted_z, device=device, dist=dist if world > 1 else None, rank=rank, world=world,
                      group=group, node_group=node_group, fuse_pupdate=fuse_pupdate, max_iters=max_iters,
-                     ax_refresh_every=ax_refresh_every, exchange=exchange, exchange_phases=exchange_phases)
+                     ax_refresh_every=ax_refresh_every, exchange=exchange, exchange_phases=exchange_phases, partition=partition)
     eng._node_prec_all = node_prec
 
     print(f"Max ADMM Iteration in Block-6 B4 Loop = {max_iters}") if verbose else None

@@ -9,7 +9,7 @@ import numpy as np
 def run_rank(rank, world, port, cfg, ret):
     import torch
     import torch.distributed as dist
-    from admm_b200.sharding import build_shard_plan, phase_bounds, post_exchange
+    from admm_b200.sharding import build_shard_plan, partition_nodes, phase_bounds, post_exchange
     from oracle import oracle as O
     dist.init_process_group("gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
     try:
@@ -17,7 +17,7 @@ def run_rank(rank, world, port, cfg, ret):
         n = N * N
         G = O.make_graph(cfg["graph"], V, seed=0, p=0.4, degree=3)
         phases = cfg.get("phases", 1)
-        sp = build_shard_plan(G, world, rank, phases)
+        sp = build_shard_plan(G, world, rank, phases, partition_nodes(G, world, cfg.get("partition", "contiguous")))
         thetas = O.node_angles(M, V)
         img = O.shepp_logan(N)
         ops = {g: O.JosephOperator(N, thetas[g]) for g in sp.local_nodes}

@@ -39,6 +39,9 @@ def main():
         xn, hn = decentralized_admm(ops, sinos, G, Wl, Q, N, exchange="nccl", **kw)      # grouped send/recv
         xp, hp = decentralized_admm(ops, sinos, G, Wl, Q, N, exchange="push", **kw)      # producers store into the peers
         x2, h2 = decentralized_admm(ops, sinos, G, Wl, Q, N, exchange="nccl", exchange_phases=2, **kw)
+        xc, hc = decentralized_admm(ops, sinos, G, Wl, Q, N, partition="contiguous", **kw)   # default map: balanced min-cut
+        assert all(np.array_equal(a, b) for a, b in zip(xs, xc))          # the map moves nodes, not arithmetic
+        assert np.allclose(hs["primal"], hc["primal"], rtol=1e-10)          # (the all-reduce sums ranks' shares in another order)
         assert all(np.array_equal(a, b) for a, b in zip(xs, xp)) and hs["primal"] == hp["primal"]
         assert all(np.array_equal(a, b) for a, b in zip(xs, x2)) and hs["primal"] == h2["primal"]
         x1, h1 = decentralized_admm(ops, sinos, G, Wl, Q, N, distributed=False, **kw)

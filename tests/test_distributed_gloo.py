@@ -14,14 +14,14 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,graph,V,phases", [(2, "ring", 4, 1), (2, "er", 7, 2), (3, "regular", 6, 1),
-                                                  (3, "er", 8, 3)])
-def test_sharded_equals_single_process(world, graph, V, phases):
+@pytest.mark.parametrize("world,graph,V,phases,partition", [(2, "ring", 4, 1, "contiguous"), (2, "er", 7, 2, "mincut"),
+                                                            (3, "regular", 6, 1, "mincut"), (3, "er", 8, 3, "contiguous")])
+def test_sharded_equals_single_process(world, graph, V, phases, partition):
     """phases > 1: the exchange is posted block by block as the x-updates finish (separate send / recv row orders)."""
     import torch.multiprocessing as mp
     from dist_helpers import run_rank
     from oracle import oracle as O
-    cfg = dict(N=16, M=36, V=V, iters=12, rho=2.0, lam=0.02, graph=graph, phases=phases)
+    cfg = dict(N=16, M=36, V=V, iters=12, rho=2.0, lam=0.02, graph=graph, phases=phases, partition=partition)
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(run_rank, args=(world, _free_port(), cfg, ret), nprocs=world, join=True)

@@ -213,3 +213,34 @@ def test_phased_exchange_orders_match_on_both_sides():
                 assert {k: v[0] for k, v in sa.items()} == rb
                 for k, (e, ph) in sa.items():
                     assert sps[a].send_rows[p][ph] <= k < sps[a].send_rows[p][ph + 1]
+
+
+def test_balanced_mincut_partition():
+    """partition_nodes: deterministic, balanced, never worse than the contiguous map; ShardPlans built on it are
+    consistent (every edge held by the owners of its ends, exchange lists equal on both sides)."""
+    from admm_b200.sharding import _map_score, build_shard_plan, partition_nodes
+    from oracle import oracle as O
+    G = O.make_graph("er", 64, seed=0, p=0.1)
+    edges = graph_csr(G)[0]
+    for world in (2, 4, 8):
+        cont = partition_nodes(G, world, "contiguous")
+        assert cont == node_to_gpu(64, world)
+        nr = partition_nodes(G, world, "mincut")
+        assert nr == partition_nodes(G, world, "auto") == partition_nodes(G, world, "mincut")   # deterministic
+        assert sorted(nr.count(k) for k in range(world)) == [64 // world] * world               # balanced
+        assert nr[0] == 0
+        assert _map_score(edges, nr, world) <= _map_score(edges, cont, world)
+        assert _map_score(edges, nr, world)[1] < 0.75 * _map_score(edges, cont, world)[1]        # ER-64: a real gain
+        plans = [build_shard_plan(G, world, r, 1, nr) for r in range(world)]
+        assert sorted(g for p in plans for g in p.local_nodes) == list(range(64))
+        for e, (i, j) in enumerate(edges):
+            holders = sorted(r for r in range(world) if e in plans[r].eslot)
+            assert holders == sorted({nr[int(i)], nr[int(j)]})
+        for a in range(world):
+            for p in plans[a].peers:
+                assert plans[a].exch[p] == plans[p].exch[a]
+    assert partition_nodes(G, 1, "mincut") == [0] * 64
+    big = O.make_graph("ring", 300, seed=0)
+    assert partition_nodes(big, 4, "auto") == node_to_gpu(300, 4)                                # auto: V > 256 stays contiguous
+    with pytest.raises(ValueError):
+        partition_nodes(G, 2, "metis")
