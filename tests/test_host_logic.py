@@ -244,3 +244,32 @@ def test_balanced_mincut_partition():
     assert partition_nodes(big, 4, "auto") == node_to_gpu(300, 4)                                # auto: V > 256 stays contiguous
     with pytest.raises(ValueError):
         partition_nodes(G, 2, "metis")
+
+
+def test_block3_checker_invariants():
+    """The quantitative invariants the reference checks by hand (test_block_3_checker.py:53-124), as asserts:
+    total per-pixel edge counts (MST / chain: n(V-1); kNN: between n(V-1) and n*min(Vk, V(V-1)/2)), the harmonic
+    bound sum_p keep*Q_ij <= sum_p min(W_i, W_j), and degree conservation of the count / weight matrices."""
+    import block_3_graph_and_precisions as b3
+    A = list(GOLD["b3_A"])
+    V, n, k = len(A), A[0].shape[1], 2
+    Wi, Q = b3.make_precisions(A, q_mode="harmonic")
+    qc = b3._precompute_q_cache(V, Q)
+    for strat in ("mst", "chain", "knn"):
+        keep = b3._build_all_pixel_masks(qc, V, n, strategy=strat, k=k, seed=123)
+        count = keep.sum(axis=2).astype(np.int64)
+        wsum = np.zeros((V, V))
+        for i in range(V):
+            for j in range(V):
+                if i != j:
+                    wsum[i, j] = float(np.sum(np.where(keep[i, j], qc[(min(i, j), max(i, j))], 0.0)))
+        pairs = int(np.triu(count, 1).sum())
+        if strat == "knn":
+            assert n * (V - 1) <= pairs <= n * min(V * k, V * (V - 1) // 2)
+        else:
+            assert pairs == n * (V - 1)
+        for i in range(V):
+            for j in range(i + 1, V):
+                assert wsum[i, j] <= float(np.sum(np.minimum(Wi[i], Wi[j]))) + 1e-12
+        assert count.sum() == 2 * np.triu(count, 1).sum()
+        assert np.isclose(wsum.sum(), 2.0 * np.triu(wsum, 1).sum())
