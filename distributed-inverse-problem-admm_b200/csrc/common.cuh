@@ -131,6 +131,46 @@ __device__ __forceinline__ float lds_f32_4(unsigned addr) {  // [addr + 4]
 __device__ __forceinline__ void lds_pair(unsigned addr, float& a, float& b) {
     asm volatile("ld.shared.f32 %0, [%2];\n\tld.shared.f32 %1, [%2+4];" : "=f"(a), "=f"(b) : "r"(addr));
 }
+// ---- Blackwell packed fp32 (sm_100+): two IEEE fp32 operations per issue slot (SASS FFMA2 / FADD2 / FMUL2) on a
+// 64-bit register pair {lo, hi}.  Each lane rounds exactly like the scalar instruction, so a packed loop is
+// bit-identical to its scalar form.  ptxas folds a pair built from one scalar (pack2(s, s)) into the broadcast
+// operand form `R.F32`, and constant pairs into uniform-register / immediate operands.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 splat2(float s) { return pack2(s, s); }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2_rm(f32x2 a, f32x2 b) {   // round towards -inf (floor through the magic number)
+    f32x2 d;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // make a value opaque to the optimiser (stops it from re-deriving / re-associating loop invariants per use)
 __device__ __forceinline__ void opaque(unsigned& v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ void opaque(float& v) { asm volatile("" : "+f"(v)); }

@@ -508,11 +508,18 @@ def np_x_update(op, prec, rhs0, rhoD, mu, lam, S, C, x, d, w):
 def decentralized_admm(ops, sinograms, G, Wi_list, Qij_diag_fn, N, lam_tv=0.01, rho=1.0, max_iters=10,
                        eps_pri=1e-1, eps_dual=1e-1, phantom_true=None, node_prec=None, tv_mu=None,
                        tv_sweeps=1, cg_iters=8, weighted_z=False, uniform_q=None, stop=True,
-                       x_update_fn=None, node_subset=None):
+                       x_update_fn=None, node_subset=None, acceptance=False, max_tighten=2):
     """Array restatement of block_6_admm_loop_ver2.py:15-326 with the SCS solve (:97-176) replaced by the
     TV-split + CG x-update.  Same initialisation (:36-46), Jacobi node sweep (:81-97,187), metrics (:189-206),
     midpoint z (:210-223) [W-weighted PDF eq. (2) if ``weighted_z``], duals (:225-230), residuals (:232-264),
     stop test (:286-289) and history keys (:310-326).
+
+    ``acceptance``: restate the reference's accept / tighten-and-retry rule (:100-108, :155-176): after a solve the
+    stationarity norm |g_x,i| (:137-149) is compared with eps_target = 2/(k+1)^1.005; a node that misses it is solved
+    again (warm-started, like the re-solve of the same ``cp.Problem`` with ``warm_start=True``) with eps/5, at most
+    ``max_tighten`` = 2 more times, and ``eps_used_history`` records the eps of the accepted try (:161,170).  One
+    "solve" here is ``tv_sweeps`` x ``cg_iters`` of the TV-split + CG x-update; eps itself only labels the try.
+    ``history['tighten_history']`` holds the number of extra solves per node.
 
     ``uniform_q``: scalar q used instead of calling ``Qij_diag_fn`` (then D_i = deg_i * q).
     ``node_subset``: if given, only those nodes are x-updated (bounded CPU-baseline sample); others keep x.
@@ -538,7 +545,7 @@ def decentralized_admm(ops, sinograms, G, Wi_list, Qij_diag_fn, N, lam_tv=0.01, 
     xupd = x_update_fn or x_update
     hist = {k: [] for k in ("primal", "dual", "pri_per_node", "dual_per_node", "obj_per_node", "obj_total",
                             "mse_sino_per_node", "mse_sino_total", "img_mse_per_node", "img_mse_total",
-                            "g_norm_history", "eps_used_history", "eps_target_history")}
+                            "g_norm_history", "eps_used_history", "eps_target_history", "tighten_history")}
     phantom_vec = None if phantom_true is None else np.asarray(phantom_true, dtype=np.float64).reshape(-1)
     nodes = range(V) if node_subset is None else node_subset
     L = lib()
@@ -547,6 +554,8 @@ def decentralized_admm(ops, sinograms, G, Wi_list, Qij_diag_fn, N, lam_tv=0.01, 
         mse_i = np.zeros(V)
         tvv = np.zeros(V)
         g_norm = np.zeros(V)
+        eps_used = np.zeros(V)
+        tighten = np.zeros(V, dtype=np.int64)
         eps_target = 2.0 / ((k + 1) ** 1.005)  # block_6_admm_loop_ver2.py:101-103
         for i in nodes:
             cons = np.zeros(n)
@@ -563,21 +572,30 @@ def decentralized_admm(ops, sinograms, G, Wi_list, Qij_diag_fn, N, lam_tv=0.01, 
             deg = ptr[i + 1] - ptr[i]
             rhoD = rho * Dv if uniform_q is None else rho * deg * float(uniform_q)
             xi = x[i].copy()
-            Ax, r, tvrhs = xupd(ops[i], node_prec[i], Atb[i] + cons, rhoD, mu, lam_tv, tv_sweeps, cg_iters,
-                                xi, d[i], w[i])
+            eps_try = min(1e-2, eps_target)  # :106-108
+            tries = 0
+            while True:
+                Ax, r, tvrhs = xupd(ops[i], node_prec[i], Atb[i] + cons, rhoD, mu, lam_tv, tv_sweeps, cg_iters,
+                                    xi, d[i], w[i])
+                # a14 stationarity (:137-149) through the identity
+                #   A^T P(Ax-b) + rho(Dx - sum q v) = tvrhs - r - mu K^T K x
+                gx, gy = grad_forward(xi, N)
+                g_vec = tvrhs - r - mu * grad_T(gx, gy, N) + lam_tv * kt_subgrad(xi, N)
+                g_norm[i] = float(np.linalg.norm(g_vec))
+                if not acceptance or g_norm[i] <= eps_target or tries >= max_tighten:   # :155-172
+                    break
+                tries += 1                   # :175-176
+                eps_try /= 5.0
+            eps_used[i], tighten[i] = eps_try, tries
             new_x[i] = xi
             res = Ax - b[i]
             mse_i[i] = float(res @ res)  # :190-194
             tvv[i] = tv_canonical(xi, N)
-            # a14 stationarity (:137-149) through the identity
-            #   A^T P(Ax-b) + rho(Dx - sum q v) = tvrhs - r - mu K^T K x
-            gx, gy = grad_forward(xi, N)
-            g_vec = tvrhs - r - mu * grad_T(gx, gy, N) + lam_tv * kt_subgrad(xi, N)
-            g_norm[i] = float(np.linalg.norm(g_vec))
         x = new_x
         hist["g_norm_history"].append(g_norm)
-        hist["eps_used_history"].append(np.full(V, min(1e-2, eps_target)))
+        hist["eps_used_history"].append(eps_used)
         hist["eps_target_history"].append(np.full(V, eps_target))
+        hist["tighten_history"].append(tighten)
         hist["mse_sino_per_node"].append(mse_i.copy())
         hist["mse_sino_total"].append(float(np.sum(mse_i)))
         if phantom_vec is not None:
