@@ -52,7 +52,7 @@ class State(ctypes.Structure):
                  "xtrue", "q", "ax", "b", "scal", "part", "counter")] + [
         ("stride", ctypes.c_longlong), ("rho", ctypes.c_float), ("lam", ctypes.c_float), ("mu", ctypes.c_float),
         ("q_uniform", ctypes.c_float), ("w_parity", ctypes.c_int), ("fuse_pupdate", ctypes.c_int),
-        ("defer_tv", ctypes.c_int), ("reuse_ax", ctypes.c_int)]
+        ("defer_tv", ctypes.c_int), ("reuse_ax", ctypes.c_int), ("ctl", ctypes.c_void_p), ("masked", ctypes.c_int)]
 
 
 EDGE_FIELDS = ("xi", "xj", "yi", "yj", "z", "ai", "aj", "Wi", "Wj", "qij", "qji")  # struct admm_edge (u64 each)
@@ -70,6 +70,8 @@ def lib():
     L = ctypes.CDLL(LIB_PATH)
     vp, i, ll, d = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_double
     L.admm_version.restype = i
+    L.admm_abi_sizeof.restype = ll
+    L.admm_abi_sizeof.argtypes = [i]
     L.admm_last_error.restype = ctypes.c_char_p
     L.admm_device_count.restype = i
     L.admm_launch_count.restype = ll
@@ -91,6 +93,7 @@ def lib():
     L.admm_rhs0.argtypes = [vp, ctypes.POINTER(State), vp, vp, vp, vp, i, i, vp]
     L.admm_x_update.argtypes = [vp, ctypes.POINTER(State), i, i, i, i, vp]
     L.admm_tv_pass.argtypes = [vp, ctypes.POINTER(State), i, i, i, vp]
+    L.admm_accept.argtypes = [vp, ctypes.POINTER(State), i, i, d, i, i, vp]
     L.admm_edge_update.argtypes = [vp, ctypes.POINTER(State), vp, i, vp, vp]
     L.admm_pack.argtypes = [vp, vp, i, vp]
     L.admm_finalize.argtypes = [vp, ctypes.POINTER(State), vp, vp, vp, vp, i, i, vp, vp, vp, vp, i, vp, vp]
@@ -104,22 +107,25 @@ def lib():
     L.admm_profile_enable.argtypes = [i]
     L.admm_profile_read.argtypes = [vp, vp]
     for name in ("admm_ipc_alloc", "admm_ipc_open", "admm_ipc_close", "admm_ipc_free", "admm_grad2d_host", "admm_div2d_host", "admm_kt_subgrad_host", "admm_profile_enable", "admm_profile_read", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host", "admm_adjoint_host",
-                 "admm_rhs0", "admm_x_update", "admm_tv_pass", "admm_edge_update", "admm_pack", "admm_finalize"):
+                 "admm_rhs0", "admm_x_update", "admm_tv_pass", "admm_accept", "admm_edge_update", "admm_pack", "admm_finalize"):
         getattr(L, name).restype = i
+    if L.admm_abi_sizeof(0) != ctypes.sizeof(State):
+        raise RuntimeError(f"libadmm_b200.so admm_state is {L.admm_abi_sizeof(0)} bytes, the binding's mirror "
+                           f"{ctypes.sizeof(State)}: stale library?")
     _lib = L
     return L
 
 
-EXPORTS = ("admm_version", "admm_last_error", "admm_device_count", "admm_plan_create", "admm_plan_destroy",
+EXPORTS = ("admm_version", "admm_abi_sizeof", "admm_last_error", "admm_device_count", "admm_plan_create", "admm_plan_destroy",
            "admm_plan_info", "admm_plan_set", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host",
            "admm_adjoint_host", "admm_colnorm2_host", "admm_rhs0", "admm_x_update", "admm_edge_update", "admm_pack", "admm_finalize",
-           "admm_tv_pass", "admm_launch_count", "admm_profile_enable", "admm_profile_read", "admm_grad2d_host",
+           "admm_tv_pass", "admm_accept", "admm_launch_count", "admm_profile_enable", "admm_profile_read", "admm_grad2d_host",
            "admm_div2d_host", "admm_kt_subgrad_host", "admm_ipc_alloc", "admm_ipc_open", "admm_ipc_close", "admm_ipc_free")
 
 OPT_PACK_BLOCKS = 0
 
 KC_NAMES = ("fwd", "fwd_reduce", "back_plain", "back_hp", "back_resid0", "colnorm2", "tv", "cg_update", "p_update",
-            "sino_axpy", "sino_resid", "rhs0", "edge", "pack", "finalize", "fwd_fused")
+            "sino_axpy", "sino_resid", "rhs0", "edge", "pack", "finalize", "fwd_fused", "accept")
 
 
 def profile_enable(on: bool) -> None:

@@ -39,7 +39,8 @@ class ADMMEngine:
     def __init__(self, thetas, sinograms, G, N, D=None, det_w=2.0, lam_tv=0.01, rho=1.0, Q=None, Wi_list=None,
                  node_prec=None, tv_mu=None, tv_sweeps=1, cg_iters=8, phantom_true=None, weighted_z=False,
                  device=0, dist=None, rank=0, world=1, group=None, node_group=None, fuse_pupdate=True,
-                 max_iters=200, ax_refresh_every=10, exchange="auto", exchange_phases=None, partition="auto"):
+                 max_iters=200, ax_refresh_every=10, exchange="auto", exchange_phases=None, partition="auto",
+                 acceptance=False, max_tighten=2):
         torch = _torch()
         nat.require_cuda()
         self.torch = torch
@@ -50,6 +51,8 @@ class ADMMEngine:
         self.rho, self.lam = float(rho), float(lam_tv)
         self.mu = float(tv_mu if tv_mu is not None else rho)
         self.S, self.C = int(tv_sweeps), int(cg_iters)
+        # a14 accept / tighten-and-retry rule (block_6_admm_loop_ver2.py:100-176), decided on the device
+        self.acceptance, self.max_tighten = bool(acceptance), int(max_tighten)
         self.dist, self.rank, self.world, self.group = dist, int(rank), int(world), group
         self._G = G
         # NCCL exchange: posted in pieces, each right after the x-update of its block of nodes (hidden behind the next
@@ -61,6 +64,9 @@ class ADMMEngine:
         self.phases = 1 if (self.world == 1 or exchange != "nccl") else max(1, int(exchange_phases or 1))
         self._peer_mem = exchange  # "p2p": consumers pull from the producer's buffer; "push": producers store into the consumer's
         # node -> GPU map: balanced min-cut by default (every rank computes the same map), "contiguous", or a list
+        if self.world > G.number_of_nodes():
+            # every rank sees the same graph, so every rank raises here -- before any collective can hang
+            raise ValueError(f"{self.world} ranks but only {G.number_of_nodes()} graph nodes: a rank would own no node")
         self.node_rank = (partition_nodes(G, self.world, partition) if isinstance(partition, str)
                           else [int(r) for r in partition])
         self.sp: ShardPlan = build_shard_plan(G, self.world, self.rank, self.phases, self.node_rank)
@@ -152,9 +158,11 @@ class ADMMEngine:
         self.z = z(max(E, 1), n)
         self.y = z(max(E, 1), 2, n)
         self.sums = torch.zeros(max(E, 1), 5, dtype=torch.float64, device=self.dev)
-        self.row = torch.zeros(2 + 7 * self.Vg, dtype=torch.float64, device=self.dev)
-        self.max_iters = int(max_iters)
-        self.hist = torch.zeros(self.max_iters, 2 + 7 * self.Vg, dtype=torch.float64, device=self.dev)
+        self.ROW = 2 + 8 * self.Vg   # r2, s2 and 8 per-node blocks (admm_finalize)
+        self.row = torch.zeros(self.ROW, dtype=torch.float64, device=self.dev)
+        self.max_iters = max(1, int(max_iters))
+        self.hist = torch.zeros(self.max_iters, self.ROW, dtype=torch.float64, device=self.dev)
+        self.ctl = torch.zeros(V, 4, dtype=torch.int32, device=self.dev)   # admm_node_ctl per local node
         self.W = None
         if weighted_z:
             if Wi_list is None:
@@ -255,6 +263,7 @@ class ADMMEngine:
                 per_sm = int(os.environ.get("ADMM_B200_PUSH_BLOCKS_PER_SM", "2"))
                 nat.check(L.admm_plan_set(self.plan.handle, nat.OPT_PACK_BLOCKS, nsm * per_sm), "admm_plan_set")
             return "p2p"
+        self._release_ipc(sync=False)     # falling back to NCCL: give the IPC buffer and any mapped peers back now
         if exchange in ("p2p", "push"):
             raise RuntimeError("peer-memory exchange requested but CUDA IPC setup failed on some rank")
         return "nccl"
@@ -360,6 +369,8 @@ class ADMMEngine:
         for name in ("x", "r", "r1", "p0", "p1", "hp", "rhs0", "tvterm", "atb", "w0", "w1", "q", "ax", "b", "scal", "part",
                      "counter", "rhoD_s"):
             setattr(st, name, getattr(self, name).data_ptr())
+        st.ctl = self.ctl.data_ptr()
+        st.masked = 0
         st.rhoD_vec = self.rhoD_vec.data_ptr() if self.rhoD_vec is not None else None
         st.prec = self.prec.data_ptr() if self.prec is not None else None
         st.xtrue = self.xtrue.data_ptr() if self.xtrue is not None else None
@@ -367,7 +378,8 @@ class ADMMEngine:
         st.rho, st.lam, st.mu, st.q_uniform = self.rho, self.lam, self.mu, self.q_uniform
         st.w_parity = 0
         st.fuse_pupdate = int(fuse) if not isinstance(fuse, bool) else (2 if fuse else 0)
-        st.defer_tv = 1 if self.world > 1 else 0
+        # the a14 decision needs |g| of the TV pass before x is final, so nothing can be deferred behind the exchange
+        st.defer_tv = 1 if (self.world > 1 and not self.acceptance) else 0
 
     def _stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
@@ -384,23 +396,33 @@ class ADMMEngine:
                               self.nbr_q.data_ptr(), 0, self.V, self._stream()), "admm_rhs0")
         reqs = []
         bounds = phase_bounds(self.V, self.phases)
+        eps_target = 2.0 / ((self.k + 1) ** 1.005)          # block_6_admm_loop_ver2.py:101-103
         for ph in range(self.phases):
             for n0 in range(bounds[ph], bounds[ph + 1], self.node_group):
                 nn = min(self.node_group, bounds[ph + 1] - n0)
                 nat.check(L.admm_x_update(h, sref, n0, nn, self.S, self.C, self._stream()), "admm_x_update")
+                if self.acceptance:
+                    # :155-176 on the device: nodes whose |g| misses the target are solved again (warm start, masked
+                    # launches), at most max_tighten times; no host round trip
+                    nat.check(L.admm_accept(h, sref, n0, nn, eps_target, self.max_tighten, 1, self._stream()), "admm_accept")
+                    keep = st.reuse_ax
+                    st.masked, st.reuse_ax = 1, 1
+                    for _ in range(self.max_tighten):
+                        nat.check(L.admm_x_update(h, sref, n0, nn, self.S, self.C, self._stream()), "admm_x_update")
+                        nat.check(L.admm_accept(h, sref, n0, nn, eps_target, self.max_tighten, 0, self._stream()),
+                                  "admm_accept")
+                    st.masked, st.reuse_ax = 0, keep
             if self.phases > 1:
                 if ph == self.phases - 1 and getattr(self, "time_exchange", False):
                     self._ex_t0 = self.torch.cuda.Event(enable_timing=True)
                     self._ex_t0.record()
                 reqs += self.exchange_start(ph)   # this block's x is final: its transfer hides behind the next block
-        st.w_parity ^= ((self.S - (1 if st.defer_tv else 0)) & 1)
         return reqs
 
     def tv_phase(self):
         """The deferred last TV pass (K3) of every local node."""
         st = self.st
         nat.check(nat.lib().admm_tv_pass(self.plan.handle, ctypes.byref(st), 0, self.V, 1, self._stream()), "admm_tv_pass")
-        st.w_parity ^= 1
 
     def exchange_start(self, phase=None):
         """Pack a = x + y of this rank's cut-edge ends (of exchange phase `phase`, or all).  NCCL mode: post the grouped
@@ -461,8 +483,11 @@ class ADMMEngine:
                                   self.row.data_ptr(), self._stream()), "admm_finalize")
         if self.world > 1:
             self.dist.all_reduce(self.row, group=self.group)  # the only data collective
-        if self.k < self.max_iters:
-            self.hist[self.k].copy_(self.row)
+        if self.k >= self.hist.shape[0]:      # engine re-used past its first max_iters: grow the history buffer
+            grown = self.torch.zeros(2 * self.hist.shape[0], self.ROW, dtype=self.torch.float64, device=self.dev)
+            grown[: self.hist.shape[0]] = self.hist
+            self.hist = grown
+        self.hist[self.k].copy_(self.row)
 
     def step(self):
         reqs = self.nodes_phase()
@@ -473,7 +498,8 @@ class ADMMEngine:
                     self._ex_t0 = self.torch.cuda.Event(enable_timing=True)
                     self._ex_t0.record()
                 reqs = self.exchange_start()  # x is final: the exchange runs under the TV pass and the local edges
-            self.tv_phase()
+            if self.st.defer_tv:
+                self.tv_phase()
             if timed:
                 self._edges_timed = (self._ex_t0, self.torch.cuda.Event(enable_timing=True))
         self.edges_phase(reqs)
@@ -487,13 +513,13 @@ class ADMMEngine:
 
     def history(self, iters=None):
         """History dict with the keys of block_6_admm_loop_ver2.py:310-326 (one entry per iteration)."""
-        iters = self.k if iters is None else iters
+        iters = self.k if iters is None else min(int(iters), self.k)
         H = self.hist[:iters].cpu().numpy()
         Vg = self.Vg
         sl = lambda k: H[:, 2 + k * Vg: 2 + (k + 1) * Vg]  # noqa: E731
-        pri, dual, pen, mse, tv, gn2, img = (sl(k) for k in range(7))
-        prec = np.ones(Vg)
+        pri, dual, pen, mse, tv, gn2, img, tries = (sl(k) for k in range(8))
         out = {k: [] for k in HIST_KEYS}
+        out["tighten_history"] = []
         obj = 0.5 * self._prec_global()[None, :] * mse + self.lam * tv + 0.5 * self.rho * pen
         for k in range(iters):
             eps_target = 2.0 / ((k + 1) ** 1.005)  # block_6_admm_loop_ver2.py:101-103
@@ -508,9 +534,10 @@ class ADMMEngine:
             out["img_mse_per_node"].append(img[k].copy())
             out["img_mse_total"].append(float(np.sum(img[k])))
             out["g_norm_history"].append(np.sqrt(gn2[k]))
-            out["eps_used_history"].append(np.full(Vg, min(1e-2, eps_target)))
+            # :106-108,161,170,176: eps of the accepted try = min(1e-2, eps_target) / 5^(tries the device really spent)
+            out["eps_used_history"].append(min(1e-2, eps_target) / 5.0 ** tries[k])
             out["eps_target_history"].append(np.full(Vg, eps_target))
-        del prec
+            out["tighten_history"].append(tries[k].astype(np.int64))
         return out
 
     def _prec_global(self):
@@ -566,18 +593,25 @@ class ADMMEngine:
             seen[k] += 1
         return out
 
-    def close(self):
+    def _release_ipc(self, sync):
+        """Unmap the peers' buffers and free this rank's (`sync`: barrier so nobody unmaps while a peer still reads;
+        off on the error path, where the peers may never arrive)."""
         L = nat.lib()
-        if self.world > 1 and getattr(self, "exchange_mode", "") == "p2p":
+        if sync:
             self.torch.cuda.synchronize(self.dev)
-            self.dist.barrier(group=self.group)      # nobody unmaps while a peer may still read
-            for ptr in self._ipc_opened:
-                L.admm_ipc_close(ctypes.c_void_p(ptr))
-            self._ipc_opened = []
             self.dist.barrier(group=self.group)
-            if self._ipc_mine:
-                L.admm_ipc_free(ctypes.c_void_p(self._ipc_mine))
-                self._ipc_mine = None
+        for ptr in getattr(self, "_ipc_opened", []):
+            L.admm_ipc_close(ctypes.c_void_p(ptr))
+        self._ipc_opened = []
+        if sync:
+            self.dist.barrier(group=self.group)
+        if getattr(self, "_ipc_mine", None):
+            L.admm_ipc_free(ctypes.c_void_p(self._ipc_mine))
+            self._ipc_mine = None
+
+    def close(self, sync=True):
+        if self.world > 1 and (getattr(self, "_ipc_mine", None) or getattr(self, "_ipc_opened", None)):
+            self._release_ipc(sync and getattr(self, "exchange_mode", "") == "p2p")
         self.plan.close()
 
 

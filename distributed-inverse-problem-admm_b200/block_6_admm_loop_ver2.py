@@ -49,12 +49,17 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                        cg_iters=8, tv_sweeps=1, tv_mu=None, node_prec=None, weighted_z=False, scs_eps=None,
                        check_every=1, node_group=None, fuse_pupdate=True, device=None, return_engine=False,
                        distributed=None, ax_refresh_every=10, exchange="auto", gather="all", exchange_phases=None, partition="auto",
+                       acceptance=True, max_tighten=2,
                        **kwargs):
     """Returns x_per_node as list of reconstructions, each length n, and the history of residual norms
     (block_6_admm_loop_ver2.py:21-24).
 
     `max_inner_iters` caps the CG iterations per TV sweep (it is unused in the reference, :17); `cg_iters`,
-    `tv_sweeps`, `tv_mu` select the inner work, which is fixed per outer iteration (no host round trips).
+    `tv_sweeps`, `tv_mu` select the work of ONE inner solve.  `acceptance` (default on, like the reference) applies
+    the accept / tighten-and-retry rule of :100-108,155-176 on the device: after a solve the stationarity norm
+    |g_x,i| (:137-149) is compared with eps_target = 2/(k+1)^1.005; a node that misses it is solved again, warm
+    started, at most `max_tighten` = 2 more times (masked launches, no host round trip); `eps_used_history` holds the
+    eps label of the accepted try (min(1e-2, eps_target) / 5^tries) and `history["tighten_history"]` the tries.
     `Qij_diag_fn` may be a callable (i, j) -> n-vector (block_3 provider), a scalar, or None (uniform 1).
     Under torch.distributed (NCCL) the nodes are sharded over the ranks; every rank returns the full result
     (`distributed=False` keeps the whole graph on this rank's GPU).  `exchange`: "p2p" reads the cut-edge iterates
@@ -99,45 +104,54 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                      cg_iters=min(int(cg_iters), int(max_inner_iters)), phantom_true=phantom_true,
                      weighted_z=weighted_z, device=device, dist=dist if world > 1 else None, rank=rank, world=world,
                      group=group, node_group=node_group, fuse_pupdate=fuse_pupdate, max_iters=max_iters,
-                     ax_refresh_every=ax_refresh_every, exchange=exchange, exchange_phases=exchange_phases, partition=partition)
+                     ax_refresh_every=ax_refresh_every, exchange=exchange, exchange_phases=exchange_phases, partition=partition,
+                     acceptance=acceptance, max_tighten=max_tighten)
     eng._node_prec_all = node_prec
 
-    print(f"Max ADMM Iteration in Block-6 B4 Loop = {max_iters}") if verbose else None
+    def _solve_and_collect():
+        print(f"Max ADMM Iteration in Block-6 B4 Loop = {max_iters}") if verbose else None
 
-    def snapshot(k, e):  # :269-281 (npy only; PNGs need matplotlib, which the hot path does not import)
-        if snapshot_dir is not None and ((k + 1) % snapshot_every == 0):
-            xs = e.x_all()                      # collective when sharded: every rank takes part
-            if rank == 0:
-                for i, xi in enumerate(xs):
-                    np.save(os.path.join(snapshot_dir, f"iter_{k+1:04d}_node_{i}.npy"), xi.reshape(N, N))
+        def snapshot(k, e):  # :269-281 (npy only; PNGs need matplotlib, which the hot path does not import)
+            if snapshot_dir is not None and ((k + 1) % snapshot_every == 0):
+                xs = e.x_all()                      # collective when sharded: every rank takes part
+                if rank == 0:
+                    for i, xi in enumerate(xs):
+                        np.save(os.path.join(snapshot_dir, f"iter_{k+1:04d}_node_{i}.npy"), xi.reshape(N, N))
 
-    t0 = time.perf_counter()
-    iters = solve(eng, max_iters, eps_pri, eps_dual, verbose=verbose, stop=True, check_every=check_every,
-                  snapshot=snapshot if snapshot_dir is not None else None)
-    t1 = time.perf_counter()
-    x = eng.x_all(gather)
-    t2 = time.perf_counter()
-    history = eng.history(iters)
-    # aliases used by the skeleton (block_6_admm_loop.py:101-105) and by the older drivers (block_7_main_ver0/1)
-    history["primal_res"], history["dual_res"], history["obj"] = history["primal"], history["dual"], history["obj_total"]
-    for key in ("pri_per_node", "dual_per_node", "obj_per_node", "obj_total"):
-        history[key + "_history"] = history[key]
-    history["wall_time_s"] = time.perf_counter() - t0
-    history["timing_s"] = {"setup": t0 - t_start, "iterations": t1 - t0, "download_x": t2 - t1,
-                           "history": time.perf_counter() - t2}
-    history["inner"] = {"cg_iters": eng.C, "tv_sweeps": eng.S, "tv_mu": eng.mu}
+        t0 = time.perf_counter()
+        iters = solve(eng, max_iters, eps_pri, eps_dual, verbose=verbose, stop=True, check_every=check_every,
+                      snapshot=snapshot if snapshot_dir is not None else None)
+        t1 = time.perf_counter()
+        x = eng.x_all(gather)
+        t2 = time.perf_counter()
+        history = eng.history(iters)
+        # aliases used by the skeleton (block_6_admm_loop.py:101-105) and by the older drivers (block_7_main_ver0/1)
+        history["primal_res"], history["dual_res"], history["obj"] = history["primal"], history["dual"], history["obj_total"]
+        for key in ("pri_per_node", "dual_per_node", "obj_per_node", "obj_total"):
+            history[key + "_history"] = history[key]
+        history["wall_time_s"] = time.perf_counter() - t0
+        history["timing_s"] = {"setup": t0 - t_start, "iterations": t1 - t0, "download_x": t2 - t1,
+                               "history": time.perf_counter() - t2}
+        history["inner"] = {"cg_iters": eng.C, "tv_sweeps": eng.S, "tv_mu": eng.mu, "acceptance": eng.acceptance,
+                            "max_tighten": eng.max_tighten}
 
-    try:  # :293-306
-        log_dir = snapshot_dir if snapshot_dir is not None else None
-        if log_dir is not None and rank == 0:
-            with open(os.path.join(log_dir, "admm_internal_params.txt"), "w") as f:
-                f.write("===== ADMM Internal Parameters =====\n")
-                f.write(f"rho = {rho}\nlambda_tv = {lam_tv}\nNumber of nodes = {num_nodes}\n")
-                f.write(f"cg_iters = {eng.C}\ntv_sweeps = {eng.S}\ntv_mu = {eng.mu}\n")
-    except Exception as e:  # pragma: no cover
-        print(f"[WARN] Could not save internal params: {e}")
+        try:  # :293-306
+            log_dir = snapshot_dir if snapshot_dir is not None else None
+            if log_dir is not None and rank == 0:
+                with open(os.path.join(log_dir, "admm_internal_params.txt"), "w") as f:
+                    f.write("===== ADMM Internal Parameters =====\n")
+                    f.write(f"rho = {rho}\nlambda_tv = {lam_tv}\nNumber of nodes = {num_nodes}\n")
+                    f.write(f"cg_iters = {eng.C}\ntv_sweeps = {eng.S}\ntv_mu = {eng.mu}\n")
+        except Exception as e:  # pragma: no cover
+            print(f"[WARN] Could not save internal params: {e}")
 
-    if return_engine:
-        return x, history, eng
-    eng.close()
-    return x, history
+        if return_engine:
+            return x, history, eng
+        eng.close()
+        return x, history
+
+    try:
+        return _solve_and_collect()
+    except BaseException:
+        eng.close(sync=False)   # never leak CUDA-IPC mappings; no barrier -- the peers may not be coming
+        raise

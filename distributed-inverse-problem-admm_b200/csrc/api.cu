@@ -15,6 +15,7 @@ static_assert(ADMM_NSCAL == NSCAL, "scalar table width");
 static_assert(ADMM_KC_COUNT == admm::KC_COUNT, "kernel class count");
 static_assert(sizeof(admm_edge) == sizeof(EdgeDesc), "edge descriptor layout");
 static_assert(sizeof(admm_pack_item) == sizeof(PackDesc), "pack descriptor layout");
+static_assert(sizeof(admm_node_ctl) == sizeof(NodeCtl), "node control layout");
 
 namespace admm {
 long long g_launch_count = 0;
@@ -89,7 +90,16 @@ struct admm_plan {
     int pack_blocks = 0;             // ADMM_OPT_PACK_BLOCKS (0: one block row per item)
 };
 
-extern "C" int admm_version(void) { return 100; }
+extern "C" int admm_version(void) { return 200; }
+extern "C" long long admm_abi_sizeof(int what) {
+    switch (what) {
+        case 0: return (long long)sizeof(admm_state);
+        case 1: return (long long)sizeof(admm_edge);
+        case 2: return (long long)sizeof(admm_pack_item);
+        case 3: return (long long)sizeof(admm_node_ctl);
+    }
+    return -1;
+}
 extern "C" const char* admm_last_error(void) { return g_err.c_str(); }
 extern "C" long long admm_launch_count(void) { return admm::g_launch_count; }
 extern "C" int admm_device_count(void) {
@@ -373,6 +383,7 @@ extern "C" int admm_rhs0(admm_plan* p, const admm_state* s, const int* d_nbr_ptr
 static TvParams make_tv(const admm_plan* p, const admm_state* s, int node0, bool diag, int parity) {
     TvParams T{};
     const long long off = (long long)node0 * s->stride;
+    if (s->ctl) parity = 0;   // the per-node parity lives in ctl[node].wpar and is applied (and flipped) by the kernel
     const float* win = parity ? s->w1 : s->w0;
     float* wout = parity ? s->w0 : s->w1;
     T.x = s->x + off; T.w_in = win + 2 * off; T.w_out = wout + 2 * off; T.tvterm = s->tvterm + off;
@@ -380,6 +391,7 @@ static TvParams make_tv(const admm_plan* p, const admm_state* s, int node0, bool
     T.lam = s->lam; T.mu = s->mu;
     T.part = s->part + (long long)node0 * admm_plan_info(p, ADMM_INFO_PART_FLOATS);
     T.counter = s->counter + node0; T.scal = s->scal;
+    T.ctl = reinterpret_cast<NodeCtl*>(s->ctl); T.masked = (s->ctl && s->masked) ? 1 : 0;
     return T;
 }
 
@@ -404,18 +416,22 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
     SinoParams SP{};
     SP.q = s->q; SP.ax = s->ax; SP.b = s->b; SP.anode = p->d_anode; SP.aptr = p->d_aptr; SP.A0 = A0; SP.A1 = A1;
     SP.D = p->D; SP.node0 = node0; SP.scal = s->scal;
+    // a14 retry pass: every kernel of the solve skips the nodes that were accepted already
+    const NodeCtl* mask = (s->ctl && s->masked) ? reinterpret_cast<const NodeCtl*>(s->ctl) : nullptr;
+    SP.ctl = mask;
 
     int parity = s->w_parity;  // the caller flips st->w_parity (sweeps & 1) once every node group is done
     for (int sw = 0; sw < sweeps; ++sw) {
         // r = rhs0 + tvterm - H x ; p = r ; rr -> S_RR0 ; ax = A x
         if (!(s->reuse_ax || sw > 0)) {   // later sweeps: ax is current by the recurrence
             FwdParams F = make_fwd(p, s->x + off, s->stride, node0);
+            F.ctl = mask;
             CK(launch_forward(F, nodes, p->max_chunks, make_red(p, s->ax, node0, nodes), st));
         }
         BackParams B = make_back(p, s->ax, s->prec, s->r + off, s->stride, node0);
         B.v = s->x + off; B.rhoD_vec = s->rhoD_vec ? s->rhoD_vec + off : nullptr; B.rhoD_s = s->rhoD_s; B.mu = s->mu;
         B.rhs0 = s->rhs0 + off; B.tvterm = s->tvterm + off; B.p_out = s->p0 + off;
-        B.part = part; B.counter = counter; B.scal = s->scal; B.dot_slot = S_RR0;
+        B.part = part; B.counter = counter; B.scal = s->scal; B.dot_slot = S_RR0; B.ctl = mask;
         CK(launch_back(BACK_RESID0, B, nodes, st));
         int cur = 0;
         float* rcur = s->r + off;            // residual buffer currently holding r (fuse 2 ping-pongs r / r1)
@@ -429,31 +445,34 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
                 FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
                 Fp.mode = 2; Fp.r = rcur; Fp.r_out = roth; Fp.p_out = poth; Fp.hp = s->hp + off; Fp.x_io = s->x + off;
                 Fp.scal = s->scal; Fp.beta_den = rr_out /* slot of the previous <r,r> */; Fp.rr_out = rr_in;
-                Fp.part = part; Fp.counter = counter;
+                Fp.part = part; Fp.counter = counter; Fp.ctl = mask;
                 CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
                 cur ^= 1; pcur = poth; rcur = roth;
             } else if (it > 0 && s->fuse_pupdate == 1) {
                 FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
                 Fp.mode = 1; Fp.r = s->r + off; Fp.p_out = poth; Fp.scal = s->scal; Fp.beta_num = rr_in; Fp.beta_den = rr_out;
+                Fp.ctl = mask;
                 CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
                 cur ^= 1; pcur = poth;
             } else if (it > 0) {
                 CgParams U{};
                 U.r = s->r + off; U.p = pcur; U.p_out = poth; U.stride = s->stride; U.n = n; U.node0 = node0;
                 U.rr_in = rr_out; U.rr_out = rr_in;  // beta = scal[rr_in(it)] / scal[rr_out(it)] = new / old
-                U.scal = s->scal;
+                U.scal = s->scal; U.ctl = mask;
                 CK(launch_p_update(U, nodes, st));
                 cur ^= 1; pcur = poth;
                 FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
+                Fp.ctl = mask;
                 CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
             } else {
                 FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
+                Fp.ctl = mask;
                 CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
             }
             BackParams H = make_back(p, s->q, s->prec, s->hp + off, s->stride, node0);
             H.v = pcur; H.rhoD_vec = B.rhoD_vec; H.rhoD_s = s->rhoD_s; H.mu = s->mu;
             H.rvec = (s->fuse_pupdate == 2) ? rcur : nullptr;
-            H.part = part; H.counter = counter; H.scal = s->scal; H.dot_slot = S_PHP;
+            H.part = part; H.counter = counter; H.scal = s->scal; H.dot_slot = S_PHP; H.ctl = mask;
             CK(launch_back(BACK_HP, H, nodes, st));
             SP.mode = 1; SP.rr_in = rr_in;
             CK(launch_sino_axpy(SP, st));
@@ -464,7 +483,7 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
                 CgParams U{};
                 U.x = s->x + off; U.r = s->r + off; U.r_in = rcur; U.p = pcur; U.hp = s->hp + off; U.stride = s->stride;
                 U.n = n; U.node0 = node0; U.rr_in = rr_in; U.rr_out = rr_out; U.part = part; U.counter = counter;
-                U.scal = s->scal;
+                U.scal = s->scal; U.ctl = mask;
                 long long nb = (n / 4 + 256 * 4 - 1) / (256 * 4);
                 nb = std::max(1LL, std::min(nb, 4096LL));
                 CK(launch_cg_update(U, nodes, (int)nb, st));
@@ -476,6 +495,17 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
         }
     }
     CK(launch_sino_resid(SP, nodes, st));
+    return ADMM_OK;
+}
+
+extern "C" int admm_accept(admm_plan* p, admm_state* s, int node0, int nodes, double eps_target, int max_tighten,
+                           int first, void* stream) {
+    if (int e = check_nodes(p, node0, nodes)) return e;
+    if (!s || !s->ctl) return fail(ADMM_ERR_ARG, "admm_accept: the state has no node control table");
+    AcceptParams A{};
+    A.ctl = reinterpret_cast<NodeCtl*>(s->ctl); A.scal = s->scal; A.node0 = node0; A.nodes = nodes;
+    A.first = first; A.max_tighten = max_tighten; A.eps_target2 = eps_target * eps_target;
+    CK(launch_accept(A, (cudaStream_t)stream));
     return ADMM_OK;
 }
 
@@ -512,6 +542,7 @@ extern "C" int admm_finalize(admm_plan* p, const admm_state* s, const double* d_
     F.sums = d_sums; F.edge_gi = d_edge_gi; F.edge_gj = d_edge_gj; F.edge_flags = d_edge_flags; F.scal = s->scal;
     F.node_gid = d_node_gid; F.row = d_row; F.E = nedges; F.E_local = nedges_local; F.V = p->V; F.Vg = Vg; F.rho = s->rho;
     F.nbr_ptr = d_nbr_ptr; F.nbr_epos = d_nbr_epos; F.nbr_end = d_nbr_end;
+    F.ctl = reinterpret_cast<const NodeCtl*>(s->ctl);
     CK(launch_finalize(F, (cudaStream_t)stream));
     return ADMM_OK;
 }

@@ -10,7 +10,7 @@ extern long long g_launch_count;  // kernels launched by this library (bench evi
 // kernel classes for the optional CUDA-event profiler (admm_profile_* in the C ABI)
 enum KClass : int {
     KC_FWD = 0, KC_FWD_REDUCE, KC_BACK_PLAIN, KC_BACK_HP, KC_BACK_RESID0, KC_COLNORM, KC_TV, KC_CG_UPDATE,
-    KC_P_UPDATE, KC_SINO_AXPY, KC_SINO_RESID, KC_RHS0, KC_EDGE, KC_PACK, KC_FINALIZE, KC_FWD_FUSED, KC_COUNT
+    KC_P_UPDATE, KC_SINO_AXPY, KC_SINO_RESID, KC_RHS0, KC_EDGE, KC_PACK, KC_FINALIZE, KC_FWD_FUSED, KC_ACCEPT, KC_COUNT
 };
 void prof_mark(int kc, cudaStream_t st, bool begin);
 extern bool g_prof_on;
@@ -35,6 +35,13 @@ struct AngleRec {
     float inv_slope;  // major / minor, 0 when |slope| <= 1e-6 (ray parallel to the step axis)
 };
 static_assert(sizeof(AngleRec) == 40, "AngleRec layout is part of the C ABI");
+
+// Per-node control word of the a14 accept / tighten-and-retry rule (block_6_admm_loop_ver2.py:100-176), kept on the
+// device so that the retry passes need no host round trip: kernels launched with `masked` skip nodes whose
+// `active` flag is 0.  `wpar` is the node's TV-multiplier ping-pong parity (0: w0 current), flipped by the TV kernel
+// itself, so nodes that took different numbers of passes stay consistent.
+struct NodeCtl { int active, tries, wpar, pad; };
+static_assert(sizeof(NodeCtl) == 16, "NodeCtl layout is part of the C ABI");
 
 constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23 : (v + kMagic) - kMagic == rint(v) for |v| < 2^22
 constexpr int kMagicBits = 0x4B400000;
@@ -72,8 +79,9 @@ __device__ __forceinline__ void block_sum(float (&v)[K], float* red) {
 // reset by the last block so the workspace is reusable by the next launch on the same stream.
 //   part:    [nblk][K] floats for this group;  counter: one unsigned for this group.
 // Must be called by all threads of the block; v[] valid in thread 0 (output of block_sum).
+// Returns true in every thread of the last block (after the result is stored), false elsewhere.
 template <int K>
-__device__ __forceinline__ void grid_reduce_store(const float (&v)[K], float* part, unsigned* counter,
+__device__ __forceinline__ bool grid_reduce_store(const float (&v)[K], float* part, unsigned* counter,
                                                   int blk, int nblk, double* out, float* red) {
     __shared__ int s_last;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
@@ -113,6 +121,7 @@ __device__ __forceinline__ void grid_reduce_store(const float (&v)[K], float* pa
         }
         if (tid == 0) *counter = 0u;
     }
+    return s_last != 0;
 }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

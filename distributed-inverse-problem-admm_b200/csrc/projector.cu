@@ -32,6 +32,7 @@ fwd_strip_kernel(const FwdParams P) {
     float4* s_ang = reinterpret_cast<float4*>(s_win + FAC);        // [FAC] inv_major, slope, inv_slope, -
 
     const int node = P.node0 + blockIdx.y;
+    if (P.ctl && !P.ctl[node].active) return;   // a14 retry pass: this node was accepted already
     const int orient = blockIdx.z;  // 0: x-dominant list, 1: y-dominant list
     const int nTi = P.nTi, nSeg = P.nSeg, N = P.N, D = P.D, span = P.span;
     const int bx = blockIdx.x;
@@ -363,6 +364,7 @@ back_tile_kernel(const BackParams P) {
     __shared__ __align__(16) float red[96];
 
     const int node = P.node0 + blockIdx.z;
+    if (P.ctl && !P.ctl[node].active) return;   // a14 retry pass: this node was accepted already
     const int N = P.N, D = P.D, bspan = P.bspan;
     const int X0 = blockIdx.y * BTX, Y0 = blockIdx.x * BTY;
     const int tid = threadIdx.x;

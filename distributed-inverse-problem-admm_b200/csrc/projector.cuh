@@ -40,6 +40,7 @@ struct FwdParams {
     float* part;             // mode 2 reduction workspace [nodes][nTi*nSeg]
     unsigned* counter;       // [nodes]
     int rr_out;              // mode 2: slot receiving <r', r'>
+    const NodeCtl* ctl;      // masked launches (a14 retry passes): blocks of nodes with ctl[node].active == 0 exit
 };
 
 struct FwdReduceParams {
@@ -88,6 +89,7 @@ struct BackParams {
     unsigned* counter;       // [V]
     double* scal;            // [V][NSCAL]
     int dot_slot;
+    const NodeCtl* ctl;      // masked launches: skip inactive nodes (nullptr: all nodes)
 };
 
 constexpr int NSCAL = 16;  // doubles per node in the scalar table

@@ -58,14 +58,18 @@ tv_fused_kernel(const TvParams P) {
     __shared__ __align__(16) float red[96];
     const int N = P.N;
     const int node = P.node0 + blockIdx.z;
+    if (P.masked && !P.ctl[node].active) return;   // a14 retry pass: this node was accepted already
     const long long nb = (long long)blockIdx.z * P.stride;
     const long long n = (long long)N * N;
     const int r = blockIdx.y * TVY + threadIdx.y;
     const int c0 = (blockIdx.x * TVX + threadIdx.x) * 4;
     const float* __restrict__ x = P.x + nb;
-    const float* __restrict__ w1p = P.w_in + 2 * nb;
+    // device-side ping-pong parity of this node's multiplier (host parity when there is no control table): every block
+    // reads it before it arrives at the grid-reduction counter, the last block flips it after all have arrived
+    const bool swap = P.ctl && P.ctl[node].wpar;
+    const float* __restrict__ w1p = (swap ? P.w_out : P.w_in) + 2 * nb;
     const float* __restrict__ w2p = w1p + n;
-    float* __restrict__ wo1 = P.w_out + 2 * nb;
+    float* __restrict__ wo1 = (swap ? const_cast<float*>(P.w_in) : P.w_out) + 2 * nb;
     float* __restrict__ wo2 = wo1 + n;
     const float kappa = P.lam / P.mu;
     float tv = 0.f, gn2 = 0.f, img = 0.f;
@@ -195,8 +199,9 @@ tv_fused_kernel(const TvParams P) {
     float v[3] = {tv, gn2, img};
     block_sum<3>(v, red);
     const int nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
-    grid_reduce_store<3>(v, P.part + (long long)blockIdx.z * nblk * 3, P.counter + blockIdx.z, blk, nblk,
-                         P.scal + (long long)node * NSCAL + S_TV, red);
+    const bool last = grid_reduce_store<3>(v, P.part + (long long)blockIdx.z * nblk * 3, P.counter + blockIdx.z, blk,
+                                           nblk, P.scal + (long long)node * NSCAL + S_TV, red);
+    if (last && P.ctl && threadIdx.x == 0 && threadIdx.y == 0) P.ctl[node].wpar ^= 1;
 }
 
 // =================================================================================================
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(256)
 cg_update_kernel(const CgParams P) {
     __shared__ __align__(16) float red[64];
     const int node = P.node0 + blockIdx.y;
+    if (P.ctl && !P.ctl[node].active) return;
     const double* sc = P.scal + (long long)node * NSCAL;
     const double php = sc[S_PHP], rr = sc[P.rr_in];
     const float alpha = (php > 0.0) ? (float)(rr / php) : 0.f;
@@ -241,6 +247,7 @@ cg_update_kernel(const CgParams P) {
 __global__ void __launch_bounds__(256)
 p_update_kernel(const CgParams P) {
     const int node = P.node0 + blockIdx.y;
+    if (P.ctl && !P.ctl[node].active) return;
     const double* sc = P.scal + (long long)node * NSCAL;
     const double den = sc[P.rr_in], num = sc[P.rr_out];
     const float beta = (den > 0.0) ? (float)(num / den) : 0.f;
@@ -262,6 +269,7 @@ __global__ void __launch_bounds__(256)
 sino_axpy_kernel(const SinoParams P) {
     const int a = P.A0 + blockIdx.x;            // angle rows on grid.x
     const int node = P.anode[a];
+    if (P.ctl && !P.ctl[node].active) return;
     const double* sc = P.scal + (long long)node * NSCAL;
     float alpha = 1.f;
     if (P.mode == 1) {
@@ -444,7 +452,7 @@ pack_kernel(const PackParams P) {
 
 // Per-iteration bookkeeping (block_6_admm_loop_ver2.py:232-264): fold the per-edge sums (in G.edges()
 // order, fp64, like the reference's Python floats) and the per-node scalars into one history row
-//   row = [r2, s2, pri_node[Vg], dual_node[Vg], pen[Vg], mse[Vg], tv[Vg], gn2[Vg], img[Vg]]
+//   row = [r2, s2, pri_node[Vg], dual_node[Vg], pen[Vg], mse[Vg], tv[Vg], gn2[Vg], img[Vg], tighten_tries[Vg]]
 // Rows of different ranks are summed by the caller (ncclAllReduce) when nodes are sharded.
 __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams P) {
     __shared__ double red2[2][8];
@@ -452,8 +460,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams P) {
     double* row = P.row;
     double* pri = row + 2; double* dual = pri + Vg; double* pen = dual + Vg;
     double* mse = pen + Vg; double* tv = mse + Vg; double* gn2 = tv + Vg; double* img = gn2 + Vg;
+    double* tries = img + Vg;
     const double rho2 = (double)P.rho * (double)P.rho;
-    for (int i = tid; i < 2 + 7 * Vg; i += blockDim.x) row[i] = 0.0;
+    for (int i = tid; i < 2 + 8 * Vg; i += blockDim.x) row[i] = 0.0;
     __syncthreads();
     // per local node, over its incident edges in G.neighbors() order
     for (int v = tid; v < P.V; v += blockDim.x) {
@@ -469,6 +478,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams P) {
         const double* sc = P.scal + (long long)v * NSCAL;
         pri[g] = a; pen[g] = b; dual[g] = d;
         mse[g] = sc[S_MSE]; tv[g] = sc[S_TV]; gn2[g] = sc[S_GN2]; img[g] = sc[S_IMG];
+        tries[g] = P.ctl ? (double)P.ctl[v].tries : 0.0;
     }
     // totals: fixed-order strided partials + fixed tree
     double r2 = 0.0, s2 = 0.0;
@@ -496,6 +506,23 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams P) {
             if ((fl & 4) && !(fl & 2)) dual[P.edge_gj[e]] += rho2 * P.sums[(long long)e * 5 + 2];
         }
     }
+}
+
+// a14 acceptance (block_6_admm_loop_ver2.py:155-176), one thread per node, after a solve + TV pass left |g_x,i|^2 in
+// scal[S_GN2]:  accept if |g| <= eps_target (:155) or the tighten cap is reached (:164); else tighten and retry (:175).
+// `first`: this is the decision after the iteration's first solve (every node took part in it).
+__global__ void __launch_bounds__(128) accept_kernel(const AcceptParams P) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= P.nodes) return;
+    NodeCtl c = P.ctl[P.node0 + v];
+    if (P.first) { c.active = 1; c.tries = 0; }
+    if (c.active) {
+        const double gn2 = P.scal[(long long)(P.node0 + v) * NSCAL + S_GN2];
+        if (gn2 <= P.eps_target2 || c.tries >= P.max_tighten) c.active = 0;
+        else c.tries += 1;
+    }
+    P.ctl[P.node0 + v].active = c.active;
+    P.ctl[P.node0 + v].tries = c.tries;
 }
 
 // ---- launchers --------------------------------------------------------------------------------------
@@ -541,6 +568,11 @@ cudaError_t launch_pack(const PackParams& P, int nitems, int narrow_blocks, cuda
     if (nitems <= 0) return cudaSuccess;
     const dim3 grid = narrow_blocks > 0 ? dim3(narrow_blocks, 1) : dim3(stream_blocks(P.n, 4), nitems);
     { ProfScope ps(KC_PACK, st); pack_kernel<<<grid, 256, 0, st>>>(P); }
+    return cudaGetLastError();
+}
+cudaError_t launch_accept(const AcceptParams& P, cudaStream_t st) {
+    if (P.nodes <= 0) return cudaSuccess;
+    { ProfScope ps(KC_ACCEPT, st); accept_kernel<<<(P.nodes + 127) / 128, 128, 0, st>>>(P); }
     return cudaGetLastError();
 }
 cudaError_t launch_finalize(const FinalizeParams& P, cudaStream_t st) {

@@ -15,6 +15,8 @@ struct TvParams {
     int node0, N;
     float lam, mu;
     float* part; unsigned* counter; double* scal;
+    NodeCtl* ctl;          // per-node w parity (flipped here) / active mask; nullptr: host parity, all nodes
+    int masked;            // 1: skip nodes with ctl[node].active == 0
 };
 
 struct CgParams {
@@ -23,6 +25,7 @@ struct CgParams {
     long long stride, n;
     int node0, rr_in, rr_out;
     float* part; unsigned* counter; double* scal;
+    const NodeCtl* ctl;    // masked launches: skip inactive nodes (nullptr: all nodes)
 };
 
 struct SinoParams {
@@ -31,6 +34,13 @@ struct SinoParams {
     const int* aptr;       // [V+1]
     int A0, A1, D, node0, mode, rr_in;   // mode 0: ax = q ; 1: ax += alpha q
     double* scal;
+    const NodeCtl* ctl;    // masked launches: skip inactive nodes (nullptr: all nodes)
+};
+
+struct AcceptParams {      // a14 acceptance decision (block_6_admm_loop_ver2.py:155-176), one thread per node
+    NodeCtl* ctl; const double* scal;
+    int node0, nodes, first, max_tighten;
+    double eps_target2;    // eps_target^2, eps_target = 2 / (k+1)^1.005 (:101-103)
 };
 
 struct RhsParams {
@@ -73,7 +83,8 @@ struct FinalizeParams {
     const int* nbr_ptr;       // [V+1] incident-edge lists of the local nodes (G.neighbors order)
     const int* nbr_epos;      // [nnz] position of the edge in the sums / flags arrays
     const int* nbr_end;       // [nnz] 0: the node is the edge's min end, 1: max end
-    double* row;              // [2 + 7*Vg]
+    const NodeCtl* ctl;       // [V] or nullptr: tries of the a14 rule -> row block 7
+    double* row;              // [2 + 8*Vg]
     int E, E_local, V, Vg;    // edges [E_local, E) are the cut edges
     float rho;
 };
@@ -89,5 +100,6 @@ cudaError_t launch_rhs0(const RhsParams& P, int nodes, cudaStream_t st);
 cudaError_t launch_edges(const EdgeParams& P, int nedges, int nblk, cudaStream_t st);
 cudaError_t launch_pack(const PackParams& P, int nitems, int narrow_blocks, cudaStream_t st);
 cudaError_t launch_finalize(const FinalizeParams& P, cudaStream_t st);
+cudaError_t launch_accept(const AcceptParams& P, cudaStream_t st);
 
 }  // namespace admm

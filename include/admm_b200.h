@@ -74,7 +74,14 @@ typedef struct admm_state {
                                  itself (lets the cut-edge exchange start before the TV kernel)         */
     int reuse_ax;             /* 1: admm_x_update takes A x from `ax` (kept current by the CG recurrence) instead of
                                  re-projecting x for the warm-start residual; set 0 periodically to refresh   */
+    struct admm_node_ctl* ctl; /* [V] per-node control words of the a14 accept / tighten rule, or NULL.  When set, the
+                                 TV-multiplier parity is per node and device-resident (w_parity is ignored)   */
+    int masked;               /* 1: admm_x_update / admm_tv_pass skip the nodes whose ctl[].active is 0 (retry pass) */
 } admm_state;
+
+/* Per-node control word (block_6_admm_loop_ver2.py:110-113 `accepted`, `tighten_tries`): zero-initialised by the
+ * caller, written by admm_accept and by the TV kernel (wpar). */
+typedef struct admm_node_ctl { int active, tries, wpar, pad; } admm_node_ctl;
 
 /* One undirected edge (i<j) as seen by this rank; addresses are device pointers as integers. */
 typedef struct admm_edge {
@@ -83,7 +90,9 @@ typedef struct admm_edge {
 
 typedef struct admm_pack_item { unsigned long long x, y, out; } admm_pack_item;
 
-int admm_version(void);
+int admm_version(void);            /* 200: round-2 ABI (admm_state grew ctl / masked; admm_accept; history row + tries) */
+long long admm_abi_sizeof(int what); /* 0 admm_state, 1 admm_edge, 2 admm_pack_item, 3 admm_node_ctl: lets a binding check
+                                        its struct mirrors against the library it loaded */
 const char* admm_last_error(void);
 int admm_device_count(void); /* 0 when no CUDA device is visible (never throws) */
 
@@ -140,12 +149,21 @@ int admm_rhs0(admm_plan* plan, const admm_state* st, const int* d_nbr_ptr, const
 int admm_x_update(admm_plan* plan, admm_state* st, int node0, int nodes, int sweeps, int cg_iters,
                   void* stream);
 
+/* ---- a14 acceptance   block_6_admm_loop_ver2.py:100-108,155-176 ----------------------------------------------
+ * After a solve (admm_x_update incl. its TV pass, which leaves |g_x,i|^2 of :137-149 in the scalar table) decide per
+ * node ON THE DEVICE: accepted if |g| <= eps_target or `max_tighten` retries were spent, else tries += 1 and the node
+ * stays active for the next admm_x_update with st->masked = 1.  `first` = 1 for the decision after the iteration's
+ * first solve (resets active / tries of every node).  No host synchronisation. */
+int admm_accept(admm_plan* plan, admm_state* st, int node0, int nodes, double eps_target, int max_tighten,
+                int first, void* stream);
+
 /* ---- K5: edges   block_6_admm_loop_ver2.py:210-264 -------------------------------------------------------
  * d_sums[E][5] = |x_i-z'|^2, |x_j-z'|^2, |z'-z|^2, pen_i, pen_j per edge. */
 int admm_edge_update(admm_plan* plan, const admm_state* st, const admm_edge* d_edges, int nedges,
                      double* d_sums, void* stream);
 int admm_pack(admm_plan* plan, const admm_pack_item* d_items, int nitems, void* stream);
-/* history row [r2, s2, pri_node[Vg], dual_node[Vg], pen[Vg], mse[Vg], tv[Vg], gn2[Vg], img[Vg]] (doubles).
+/* history row [r2, s2, pri_node[Vg], dual_node[Vg], pen[Vg], mse[Vg], tv[Vg], gn2[Vg], img[Vg], tries[Vg]] (doubles;
+ * tries = extra solves the a14 rule spent on the node, 0 without a control table).
  * Edge arrays list the rank's local edges first (nedges_local), then its cut edges; flags: bit0 i local, bit1 j
  * local, bit2 this rank owns the edge's dual residual.  nbr_* = incident-edge CSR of the local nodes
  * (G.neighbors order): position of the edge in the edge arrays and which end the node is. */
@@ -182,8 +200,8 @@ long long admm_launch_count(void);
 
 /* optional CUDA-event profiler: one event pair per launch on the launching stream, summed per kernel class:
  * 0 fwd, 1 fwd_reduce, 2 back_plain, 3 back_hp, 4 back_resid0, 5 colnorm2, 6 tv, 7 cg_update, 8 p_update,
- * 9 sino_axpy, 10 sino_resid, 11 rhs0, 12 edge, 13 pack, 14 finalize, 15 fwd_fused(p-update) */
-#define ADMM_KC_COUNT 16
+ * 9 sino_axpy, 10 sino_resid, 11 rhs0, 12 edge, 13 pack, 14 finalize, 15 fwd_fused(p-update), 16 accept */
+#define ADMM_KC_COUNT 17
 int admm_profile_enable(int on);
 int admm_profile_read(double* ms, long long* cnt);
 

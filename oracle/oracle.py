@@ -508,13 +508,13 @@ def np_x_update(op, prec, rhs0, rhoD, mu, lam, S, C, x, d, w):
 def decentralized_admm(ops, sinograms, G, Wi_list, Qij_diag_fn, N, lam_tv=0.01, rho=1.0, max_iters=10,
                        eps_pri=1e-1, eps_dual=1e-1, phantom_true=None, node_prec=None, tv_mu=None,
                        tv_sweeps=1, cg_iters=8, weighted_z=False, uniform_q=None, stop=True,
-                       x_update_fn=None, node_subset=None, acceptance=False, max_tighten=2):
+                       x_update_fn=None, node_subset=None, acceptance=True, max_tighten=2):
     """Array restatement of block_6_admm_loop_ver2.py:15-326 with the SCS solve (:97-176) replaced by the
     TV-split + CG x-update.  Same initialisation (:36-46), Jacobi node sweep (:81-97,187), metrics (:189-206),
     midpoint z (:210-223) [W-weighted PDF eq. (2) if ``weighted_z``], duals (:225-230), residuals (:232-264),
     stop test (:286-289) and history keys (:310-326).
 
-    ``acceptance``: restate the reference's accept / tighten-and-retry rule (:100-108, :155-176): after a solve the
+    ``acceptance`` (default on, as in the reference): restate the reference's accept / tighten-and-retry rule (:100-108, :155-176): after a solve the
     stationarity norm |g_x,i| (:137-149) is compared with eps_target = 2/(k+1)^1.005; a node that misses it is solved
     again (warm-started, like the re-solve of the same ``cp.Problem`` with ``warm_start=True``) with eps/5, at most
     ``max_tighten`` = 2 more times, and ``eps_used_history`` records the eps of the accepted try (:161,170).  One

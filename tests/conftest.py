@@ -12,6 +12,7 @@ for p in (ROOT, PKG):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: minutes of host (oracle) time; still part of the default -m gpu run")
 
 
 def _has_cuda():

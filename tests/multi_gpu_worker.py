@@ -1,5 +1,8 @@
-"""torchrun worker: the NCCL-sharded solve must reproduce the single-GPU solve (same kernels, same per-node
-arithmetic; only the order of the fp64 residual sums changes)."""
+"""torchrun worker: the sharded solve must reproduce the single-GPU solve (same kernels, same per-node arithmetic).
+Across RANK COUNTS the agreement is a tolerance, not bit-identity: the fp64 residual sums are reduced in another order
+(<= 1e-10), and a plan holding fewer nodes may pick another forward-projector segment length, which changes the fp32
+summation order inside K1 (the 256^2 case below; SCALE_r01 showed 5.7e-9 on the residuals at 2048^2): traces must agree
+to 1e-8 relative, x to 1e-6 relative L2.  Between EXCHANGE PATHS at one rank count everything is bit-identical."""
 import os
 import sys
 
@@ -21,7 +24,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     rank, world = dist.get_rank(), dist.get_world_size()
     ok = True
-    for (N, M, V, graph, wq) in ((64, 96, 8, "er", False), (48, 60, 5, "ring", True)):
+    for (N, M, V, graph, wq) in ((64, 96, 8, "er", False), (48, 60, 5, "ring", True), (256, 96, 8, "er", False)):
         thetas = node_angles(M, V)
         img = shepp_logan(N)
         ops = [RayTransformCUDA(N, t, device=local) for t in thetas]
@@ -48,12 +51,17 @@ def main():
         assert all(np.array_equal(a, b) for a, b in zip(xs, xn)) and hs["primal"] == hn["primal"]
         cut = cut_statistics(G, world)["cut"]
         same_x = all(np.array_equal(a, b) for a, b in zip(xs, x1))
+        xd = max(float(np.linalg.norm(a - b) / np.linalg.norm(b)) for a, b in zip(xs, x1))
         tr = max(np.max(np.abs(np.array(hs[k]) - np.array(h1[k])) / np.maximum(np.abs(np.array(h1[k])), 1e-30))
-                 for k in ("primal", "dual", "pri_per_node", "dual_per_node", "mse_sino_per_node", "obj_per_node"))
-        good = same_x and tr < 1e-10 and (cut > 0 or world == 1)
+                 for k in ("primal", "dual"))
+        tn = max(np.max(np.abs(np.array(hs[k]) - np.array(h1[k])) / np.maximum(np.abs(np.array(h1[k])), 1e-30))
+                 for k in ("pri_per_node", "dual_per_node", "mse_sino_per_node", "obj_per_node"))
+        same_t = np.array_equal(np.array(hs["tighten_history"]), np.array(h1["tighten_history"]))
+        good = tr < 1e-8 and tn < 1e-6 and xd < 1e-6 and same_t and (cut > 0 or world == 1)
         ok = ok and good
         if rank == 0:
-            print(f"world {world} N {N} V {V} {graph}: cut edges {cut}, x bit-identical {same_x}, max trace rel diff {tr:.2e}")
+            print(f"world {world} vs 1 GPU, N {N} V {V} {graph}: cut edges {cut}, x bit-identical {same_x} (rel L2 diff "
+                  f"{xd:.2e}), residual traces rel diff {tr:.2e}, per-node metrics {tn:.2e}, a14 decisions identical {same_t}")
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -25,21 +25,39 @@ def _problem(N, M, V, partition="contiguous", sigma=0.005, hetero=False):
     return thetas, img, ops_o, ops_g, sinos
 
 
-def _compare(hg, ho, xg, xo, img, N, iters):
+# Secondary history keys.  North_star states tolerances for the residual traces, the final x and its PSNR only; the
+# per-node metrics are held to the same 1e-3.  |g_x,i| (block_6_admm_loop_ver2.py:137-149) is the norm of a SUM THAT
+# CANCELS -- data gradient + consensus gradient + TV subgradient are each O(10-100) x larger than g near a
+# stationary point -- so its fp32 evaluation carries that amplification of the 1e-7 rounding: 1e-2.
+NODE_TOL = 1e-3
+GNORM_TOL = 1e-2
+
+
+def _compare(hg, ho, xg, xo, img, N, iters, report=None):
     assert len(hg["primal"]) == len(ho["primal"]) == iters
     pg, po = np.array(hg["primal"]), np.array(ho["primal"])
     dg, do = np.array(hg["dual"]), np.array(ho["dual"])
-    assert np.max(np.abs(pg - po) / po) < TRACE_TOL
-    assert np.max(np.abs(dg - do) / do) < TRACE_TOL
+    err = {"primal": float(np.max(np.abs(pg - po) / po)), "dual": float(np.max(np.abs(dg - do) / do))}
     for key in ("pri_per_node", "dual_per_node", "mse_sino_per_node", "obj_per_node", "img_mse_per_node"):
         a, b = np.array(hg[key]), np.array(ho[key])
-        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-12)) < 2e-3, key
+        err[key] = float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-12)))
     a, b = np.array(hg["g_norm_history"]), np.array(ho["g_norm_history"])
-    assert np.max(np.abs(a - b) / np.maximum(b, 1e-9)) < 1e-2
+    err["g_norm"] = float(np.max(np.abs(a - b) / np.maximum(b, 1e-9)))
     from oracle import oracle as O
-    for i in range(len(xo)):
-        assert np.linalg.norm(xg[i] - xo[i]) / np.linalg.norm(xo[i]) < RECON_TOL
-        assert abs(O.psnr(xg[i].reshape(N, N), img) - O.psnr(xo[i].reshape(N, N), img)) < PSNR_TOL
+    err["x"] = float(max(np.linalg.norm(xg[i] - xo[i]) / np.linalg.norm(xo[i]) for i in range(len(xo))))
+    err["psnr_db"] = float(max(abs(O.psnr(xg[i].reshape(N, N), img) - O.psnr(xo[i].reshape(N, N), img))
+                               for i in range(len(xo))))
+    if report:
+        print(f"PARITY {report}: " + ", ".join(f"{k} {v:.2e}" for k, v in err.items()))
+    # the a14 decisions (accept / retry per node and iteration) are integer work: identical
+    assert np.array_equal(np.array(hg["tighten_history"]), np.array(ho["tighten_history"]))
+    assert np.allclose(np.array(hg["eps_used_history"]), np.array(ho["eps_used_history"]), rtol=1e-12)
+    assert err["primal"] < TRACE_TOL and err["dual"] < TRACE_TOL, err
+    for key in ("pri_per_node", "dual_per_node", "mse_sino_per_node", "obj_per_node", "img_mse_per_node"):
+        assert err[key] < NODE_TOL, (key, err)
+    assert err["g_norm"] < GNORM_TOL, err
+    assert err["x"] < RECON_TOL and err["psnr_db"] < PSNR_TOL, err
+    return err
 
 
 def test_ring_uniform_q_200_iterations():
@@ -184,25 +202,6 @@ def test_single_node_without_edges_and_isolated_node():
     assert h3["pri_per_node"][-1][1] == 0.0
 
 
-def test_cfg2_size_parity_few_iterations():
-    """BASELINE configs[1] at full size (512^2, 360 angles, 16 nodes, random 4-regular graph, uniform precisions):
-    the first outer iterations against the oracle."""
-    from admm_b200 import RayTransformCUDA, node_angles
-    from block_6_admm_loop_ver2 import decentralized_admm
-    from oracle import oracle as O
-    N, M, V, iters = 512, 360, 16, 4
-    thetas = node_angles(M, V)
-    img = O.shepp_logan(N)
-    ops_o = [O.JosephOperator(N, t) for t in thetas]
-    sinos = [(op.forward(img) + 0.005 * np.random.default_rng(1234 + i).standard_normal(op.shape[0]))
-             .reshape(op.nang, N).astype(np.float32) for i, op in enumerate(ops_o)]
-    G = O.make_graph("regular", V, seed=0, degree=4)
-    kw = dict(lam_tv=0.02, rho=2.0, max_iters=iters, eps_pri=0.0, eps_dual=0.0, phantom_true=img, cg_iters=8)
-    xo, ho = O.decentralized_admm(ops_o, sinos, G, None, None, N, uniform_q=1.0, **kw)
-    xg, hg = decentralized_admm([RayTransformCUDA(N, t) for t in thetas], sinos, G, None, None, N, verbose=False, **kw)
-    _compare(hg, ho, xg, xo, img, N, iters)
-
-
 def test_cfg4_size_iteration_is_deterministic_and_self_consistent():
     """BASELINE configs[3] at full size (2048^2, 720 angles, 64 nodes, ER graph): two runs are bit-identical (no float
     atomics anywhere), the history obeys the identities of block_6_admm_loop_ver2.py:232-264, and the first iterate
@@ -240,3 +239,82 @@ def test_cfg4_size_iteration_is_deterministic_and_self_consistent():
     O.x_update(op, 1.0, op.adjoint(sinos[i].reshape(-1).astype(np.float64)), 2.0 * G.degree(i), 2.0, 0.02, 1, 8, x, d, w)
     xg, hg = decentralized_admm(ops, sinos, G, None, None, N, **dict(kw, max_iters=1))
     assert np.linalg.norm(xg[i] - x) < 1e-3 * np.linalg.norm(x)
+
+
+# ---- BASELINE.json configs at their own sizes ----------------------------------------------------------------------
+def test_cfg1_full_size_200_iterations():
+    """BASELINE configs[0] at its real size: 128^2, 180 angles over a ring of 4, lam 0.02, rho 2, 200 outer iterations
+    with the reference's accept / tighten rule on (most iterations spend all three solves)."""
+    from block_6_admm_loop_ver2 import decentralized_admm
+    from oracle import oracle as O
+    N, M, V, iters = 128, 180, 4, 200
+    thetas, img, ops_o, ops_g, sinos = _problem(N, M, V)
+    G = O.make_graph("ring", V)
+    kw = dict(lam_tv=0.02, rho=2.0, max_iters=iters, eps_pri=0.0, eps_dual=0.0, phantom_true=img, tv_sweeps=1, cg_iters=8)
+    xo, ho = O.decentralized_admm(ops_o, sinos, G, None, None, N, uniform_q=1.0, **kw)
+    xg, hg = decentralized_admm(ops_g, sinos, G, None, None, N, verbose=False, **kw)
+    _compare(hg, ho, xg, xo, img, N, iters, report="cfg1 128^2 x200")
+    t = np.array(hg["tighten_history"])
+    assert t.max() == 2 and t.min() == 0
+
+
+def _cfg_problem_gpu_sinos(N, M, V, hetero):
+    """Inputs of the large configs: b_i = A_i x_true + sigma_i eps_i with A_i x_true from the fp64 oracle."""
+    return _problem(N, M, V, hetero=hetero)
+
+
+def test_cfg2_full_size_25_iterations():
+    """BASELINE configs[1] at full size (512^2, 360 angles, 16 nodes, random 4-regular graph, uniform precisions), 25
+    outer iterations (one solve per iteration: S=1, C=8) and, separately, 10 with the a14 rule on."""
+    from block_6_admm_loop_ver2 import decentralized_admm
+    from oracle import oracle as O
+    N, M, V = 512, 360, 16
+    thetas, img, ops_o, ops_g, sinos = _problem(N, M, V)
+    G = O.make_graph("regular", V, seed=0, degree=4)
+    for iters, acc in ((25, False), (10, True)):
+        kw = dict(lam_tv=0.02, rho=2.0, max_iters=iters, eps_pri=0.0, eps_dual=0.0, phantom_true=img, cg_iters=8,
+                  acceptance=acc)
+        xo, ho = O.decentralized_admm(ops_o, sinos, G, None, None, N, uniform_q=1.0, **kw)
+        xg, hg = decentralized_admm(ops_g, sinos, G, None, None, N, verbose=False, **kw)
+        _compare(hg, ho, xg, xo, img, N, iters, report=f"cfg2 512^2 x{iters} acceptance={acc}")
+
+
+def test_cfg3_full_size_heterogeneous_precisions():
+    """BASELINE configs[2] at full size: 1024^2, 720 angles, 32 nodes on a random 4-regular graph, heterogeneous noise
+    sigma_i = 0.005 * 2^((i mod 4) - 1) with P_i = sigma_i^-2 / max (weighted least squares), block_3's arithmetic-mean
+    Q_ij = (W_i + W_j)/2 from the column norms (block_3_graph_and_precisions.py:34-39): rhoD_vec / Qdir / prec at the
+    size where their traffic matters.  3 outer iterations against the oracle."""
+    import block_3_graph_and_precisions as b3
+    from block_6_admm_loop_ver2 import decentralized_admm
+    from oracle import oracle as O
+    N, M, V, iters = 1024, 720, 32, 3
+    thetas, img, ops_o, ops_g, sinos = _problem(N, M, V, hetero=True)
+    G = O.make_graph("regular", V, seed=0, degree=4)
+    Wo, Qo = O.make_precisions([op.colnorm2() for op in ops_o], "arithmetic")
+    Wg, Qg = b3.make_precisions(ops_g, q_mode="arithmetic")            # K2b on the device
+    for i in (0, 17, 31):
+        assert np.linalg.norm(np.asarray(Wg[i], dtype=np.float64) - Wo[i]) < 1e-4 * np.linalg.norm(Wo[i])
+    sig = np.array([0.005 * 2.0 ** ((i % 4) - 1) for i in range(V)])
+    prec = (sig ** -2) / np.max(sig ** -2)
+    kw = dict(lam_tv=0.02, rho=2.0, max_iters=iters, eps_pri=0.0, eps_dual=0.0, phantom_true=img, node_prec=prec,
+              cg_iters=8, acceptance=False)
+    xo, ho = O.decentralized_admm(ops_o, sinos, G, Wo, Qo, N, **kw)
+    xg, hg = decentralized_admm(ops_g, sinos, G, Wg, Qg, N, verbose=False, **kw)
+    _compare(hg, ho, xg, xo, img, N, iters, report="cfg3 1024^2 x3")
+
+
+@pytest.mark.slow
+def test_cfg4_full_size_two_iterations_all_nodes():
+    """BASELINE configs[3] at full size (2048^2, 720 angles, 64 nodes, Erdos-Renyi graph, 201 edges): two complete outer
+    iterations of ALL nodes and edges against the fp64 oracle (minutes of host time, ~35 GB of host memory)."""
+    from block_6_admm_loop_ver2 import decentralized_admm
+    from oracle import oracle as O
+    N, M, V, iters = 2048, 720, 64, 2
+    thetas, img, ops_o, ops_g, sinos = _problem(N, M, V)
+    G = O.make_graph("er", V, seed=0, p=0.1)
+    assert G.number_of_edges() == 201
+    kw = dict(lam_tv=0.02, rho=2.0, max_iters=iters, eps_pri=0.0, eps_dual=0.0, phantom_true=img, cg_iters=8,
+              acceptance=False)
+    xo, ho = O.decentralized_admm(ops_o, sinos, G, None, None, N, uniform_q=1.0, **kw)
+    xg, hg = decentralized_admm(ops_g, sinos, G, None, None, N, verbose=False, **kw)
+    _compare(hg, ho, xg, xo, img, N, iters, report="cfg4 2048^2 x2, 64 nodes")

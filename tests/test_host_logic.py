@@ -114,14 +114,15 @@ def test_phantoms_match_reference():
 def test_c_abi_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "admm_b200.h")).read()
     declared = set(re.findall(r"^\s*(?:const\s+)?[A-Za-z_][\w\s\*]*?\b(admm_\w+)\s*\(", hdr, flags=re.M))
-    declared -= {"admm_plan", "admm_state", "admm_edge", "admm_pack_item"}
+    declared -= {"admm_plan", "admm_state", "admm_edge", "admm_pack_item", "admm_node_ctl"}
     assert len(declared) >= 20
     L = nat.lib()
     missing = [n for n in sorted(declared) if not hasattr(L, n)]
     assert not missing, missing
     assert set(nat.EXPORTS) <= declared
-    assert L.admm_version() == 100
-    assert ctypes.sizeof(nat.State) == 21 * 8 + 8 + 4 * 4 + 4 * 4
+    assert L.admm_version() == 200
+    assert ctypes.sizeof(nat.State) == L.admm_abi_sizeof(0) == 224
+    assert L.admm_abi_sizeof(1) == 11 * 8 and L.admm_abi_sizeof(2) == 3 * 8 and L.admm_abi_sizeof(3) == 16
 
 
 def test_no_cpu_fallback_without_device():

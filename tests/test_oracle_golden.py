@@ -93,8 +93,17 @@ def test_outer_loop_matches_reference_block6(tag):
                                 eps_dual=1e-9, phantom_true=O.shepp_logan(N), tv_mu=mu, tv_sweeps=S, cg_iters=C,
                                 x_update_fn=O.np_x_update)
     for key in ("primal", "dual", "pri_per_node", "dual_per_node", "obj_per_node", "obj_total", "mse_sino_per_node",
-                "mse_sino_total", "img_mse_per_node", "img_mse_total", "eps_target_history"):
+                "mse_sino_total", "img_mse_per_node", "img_mse_total", "eps_target_history", "eps_used_history"):
         assert np.allclose(np.array(h[key]), G[f"b6_{tag}_{key}"], rtol=1e-9, atol=1e-12), key
+    # a14 (block_6_admm_loop_ver2.py:100-176): the reference really retried -- the solves it issued per (iteration,
+    # node), and the eps it handed to each, are what the oracle's restatement of the rule produces
+    solves = G[f"b6_{tag}_solve_eps"]
+    per = np.zeros((iters, len(rows)), dtype=np.int64)
+    for k, node, eps in solves:
+        assert np.isclose(eps, min(1e-2, 2.0 / ((k + 1) ** 1.005)) / 5.0 ** per[int(k), int(node)], rtol=1e-12)
+        per[int(k), int(node)] += 1
+    assert np.array_equal(per - 1, np.array(h["tighten_history"]))
+    assert per.max() == 3 and per.min() == 1          # the fixture exercises accept-at-once and the tighten cap
     assert np.allclose(np.array(h["g_norm_history"]), G[f"b6_{tag}_g_norm_history"], rtol=1e-7)
     assert np.allclose(np.stack(x), G[f"b6_{tag}_x"], rtol=1e-10, atol=1e-13)
     # the C x-update with the matrix-free projector agrees with the dense float32 matrices to fp32 rounding

@@ -8,7 +8,9 @@ solve of eq. (1), in the quantities north_star grades: per-iteration primal/dual
 cfg1  = BASELINE configs[0] at full size (128^2, 180 angles, ring of 4);
 cfg2s = BASELINE configs[1]'s shape (360 angles, 16 nodes, random 4-regular graph) at 128^2 -- the converged inner
         solve of the 512^2 problem is days of CPU time.
-The converged reference repeats (1 sweep x 25 CG) solves, warm-started, until |dx| <= 1e-9 |x| (cap 400 sweeps).
+The "converged" reference runs REF_S = 50 sweeps x REF_C = 8 CG per solve with mu = 4 rho (the inner fixed point does
+not depend on mu; 4 rho converges fastest here: per-sweep change 4e-5 |x| after 50 sweeps from a cold start, far less
+when warm-started); `--deeper` re-runs it with 100 sweeps to show what is left.
 Uses only oracle/ (test infrastructure); nothing here is on the product path.
 """
 from __future__ import annotations
@@ -34,6 +36,7 @@ CONFIGS = {
 }
 
 # name -> (S, C, acceptance, mu)
+REF_S, REF_C, REF_MU = 50, 8, 4 * RHO
 SCHEDULES = [
     ("S1C8", 1, 8, False, RHO),          # round-1 bench schedule
     ("S1C4+accept", 1, 4, True, RHO),
@@ -44,10 +47,10 @@ SCHEDULES = [
     ("S3C8", 3, 8, False, RHO),
     ("S3C30", 3, 30, False, RHO),
     ("S8C4", 8, 4, False, RHO),
-    ("S16C4", 16, 4, False, RHO),
-    ("S1C8 mu=rho/4", 1, 8, False, RHO / 4),
     ("S1C8 mu=4rho", 1, 8, False, 4 * RHO),
+    ("S2C4 mu=4rho", 2, 4, False, 4 * RHO),
     ("S4C2 mu=4rho", 4, 2, False, 4 * RHO),
+    ("S8C4 mu=4rho", 8, 4, False, 4 * RHO),
 ]
 
 
@@ -65,30 +68,19 @@ def problem(cfg):
 class Counting:
     """x-update wrapper that counts the inner work actually done."""
 
-    def __init__(self, converged=False):
+    def __init__(self):
         self.cg = 0
         self.sweeps = 0
-        self.converged = converged
 
     def __call__(self, op, prec, rhs0, rhoD, mu, lam, S, C, x, d, w):
-        if not self.converged:
-            self.cg += S * C
-            self.sweeps += S
-            return O.x_update(op, prec, rhs0, rhoD, mu, lam, S, C, x, d, w)
-        out = None
-        for _ in range(400):
-            x0 = x.copy()
-            out = O.x_update(op, prec, rhs0, rhoD, mu, lam, 1, 25, x, d, w)
-            self.cg += 25
-            self.sweeps += 1
-            if np.linalg.norm(x - x0) <= 1e-9 * max(np.linalg.norm(x), 1e-30):
-                break
-        return out
+        self.cg += S * C
+        self.sweeps += S
+        return O.x_update(op, prec, rhs0, rhoD, mu, lam, S, C, x, d, w)
 
 
-def run(cfg, iters, S, C, accept, mu, converged=False):
+def run(cfg, iters, S, C, accept, mu):
     ops, sinos, G, img = problem(cfg)
-    cnt = Counting(converged)
+    cnt = Counting()
     t = time.perf_counter()
     x, h = O.decentralized_admm(ops, sinos, G, None, None, cfg["N"], lam_tv=LAM, rho=RHO, max_iters=iters,
                                 eps_pri=0.0, eps_dual=0.0, phantom_true=img, tv_mu=mu, tv_sweeps=S, cg_iters=C,
@@ -102,6 +94,7 @@ def main():
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_inner_schedule_study.json"))
     ap.add_argument("--schedules", default="")
+    ap.add_argument("--deeper", action="store_true", help="also run the reference with 2x the sweeps")
     args = ap.parse_args()
     want = [s for s in args.schedules.split(",") if s]
     out = {}
@@ -110,18 +103,21 @@ def main():
     for cname in args.configs.split(","):
         cfg = CONFIGS[cname]
         V, N = cfg["V"], cfg["N"]
-        xr, hr, cr, tr, img = run(cfg, args.iters, 1, 25, False, RHO, converged=True)
+        xr, hr, cr, tr, img = run(cfg, args.iters, REF_S, REF_C, False, REF_MU)
         pr, dr = np.array(hr["primal"]), np.array(hr["dual"])
         res = out.setdefault(cname, {})
         res["_config"] = {k: (v if not isinstance(v, tuple) else list(v)) for k, v in cfg.items()}
         res["_config"].update(lam_tv=LAM, rho=RHO, sigma=SIGMA, iters=args.iters)
-        res["converged"] = {"cg_per_node_iter": cr.cg / (V * args.iters), "sweeps_per_node_iter": cr.sweeps / (V * args.iters),
+        res["converged"] = {"S": REF_S, "C": REF_C, "tv_mu": REF_MU, "cg_per_node_iter": cr.cg / (V * args.iters), "sweeps_per_node_iter": cr.sweeps / (V * args.iters),
                             "final_primal": float(pr[-1]), "final_dual": float(dr[-1]),
                             "psnr_node0": float(O.psnr(xr[0].reshape(N, N), img)), "wall_s": round(tr, 1),
                             "g_norm_last": [float(v) for v in hr["g_norm_history"][-1]],
                             "eps_target_last": float(hr["eps_target_history"][-1][0])}
         print(cname, "converged:", res["converged"], flush=True)
-        for name, S, C, acc, mu in SCHEDULES:
+        scheds = list(SCHEDULES)
+        if args.deeper:
+            scheds.insert(0, ("reference x2 sweeps", 2 * REF_S, REF_C, False, REF_MU))
+        for name, S, C, acc, mu in scheds:
             if want and name not in want:
                 continue
             x, h, cnt, t, _ = run(cfg, args.iters, S, C, acc, mu)
