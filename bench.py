@@ -266,7 +266,7 @@ def run_reference(args, cfg, rank):
 def workload_config(args, cfg, G):
     c = {"workload": f"{args.config}: {cfg['desc']}", "N": cfg["N"], "angles": cfg["M"], "nodes": total_nodes(cfg),
          "graph": cfg["graph"], "lam_tv": LAM, "rho": RHO, "tv_mu": RHO, "tv_sweeps": args.tv_sweeps,
-         "cg_iters": args.cg_iters, "noise_sigma": SIGMA,
+         "cg_iters": args.cg_iters, "acceptance": bool(getattr(args, "acceptance", 0)), "noise_sigma": SIGMA,
          "partition": "single GPU" if args.gpus == 1 else getattr(args, "partition_used", args.partition),
          "inputs_larger_than_L2": True, "stop_test": "disabled in the timed region"}
     if args.gpus > 1:
@@ -293,6 +293,10 @@ def main():
                     help="node -> GPU map when sharded (auto: balanced min-cut for <= 256 nodes)")
     ap.add_argument("--exchange-phases", type=int, default=None,
                     help="NCCL exchange: post the cut-edge transfers in this many pieces per iteration (default 2)")
+    ap.add_argument("--acceptance", type=int, default=0, choices=[0, 1],
+                    help="1: the reference's accept / tighten-and-retry rule (block_6_ver2:100-176) on the device: up to "
+                         "3 solves of tv_sweeps x cg_iters per node and iteration")
+    ap.add_argument("--no-carry", action="store_true", help="rebuild the CG residual with a back-projection at every solve")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="no per-kernel CUDA events in the timed region")
@@ -331,7 +335,8 @@ def main():
     eng = ADMMEngine(thetas, sinos, G, cfg["N"], lam_tv=LAM, rho=RHO, Q=Q, Wi_list=Wl, node_prec=node_prec(cfg),
                      tv_sweeps=S, cg_iters=C, phantom_true=img, device=local, dist=dist if world > 1 else None,
                      rank=rank, world=world, node_group=args.node_group or None, fuse_pupdate=not args.no_fuse,
-                     max_iters=total, exchange=args.exchange, exchange_phases=args.exchange_phases, partition=args.partition)
+                     max_iters=total, exchange=args.exchange, exchange_phases=args.exchange_phases, partition=args.partition,
+                     acceptance=bool(args.acceptance), carry_residual=not args.no_carry)
 
     args.exchange_used = "push" if (eng.exchange_mode == "p2p" and getattr(eng, "_push", False)) else eng.exchange_mode
     args.phases_used = eng.phases
@@ -474,7 +479,8 @@ def main():
                                           cg_iters=C, tv_sweeps=S, node_prec=node_prec(cfg), device=local,
                                           node_group=args.node_group or None, fuse_pupdate=not args.no_fuse,
                                           return_engine=True, exchange=args.exchange, gather="rank0",
-                                          exchange_phases=args.exchange_phases, partition=args.partition)
+                                          exchange_phases=args.exchange_phases, partition=args.partition,
+                                          acceptance=bool(args.acceptance), carry_residual=not args.no_carry)
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:

@@ -52,7 +52,8 @@ class State(ctypes.Structure):
                  "xtrue", "q", "ax", "b", "scal", "part", "counter")] + [
         ("stride", ctypes.c_longlong), ("rho", ctypes.c_float), ("lam", ctypes.c_float), ("mu", ctypes.c_float),
         ("q_uniform", ctypes.c_float), ("w_parity", ctypes.c_int), ("fuse_pupdate", ctypes.c_int),
-        ("defer_tv", ctypes.c_int), ("reuse_ax", ctypes.c_int), ("ctl", ctypes.c_void_p), ("masked", ctypes.c_int)]
+        ("defer_tv", ctypes.c_int), ("reuse_ax", ctypes.c_int), ("ctl", ctypes.c_void_p), ("masked", ctypes.c_int),
+        ("carry_r", ctypes.c_int), ("reuse_r", ctypes.c_int)]
 
 
 EDGE_FIELDS = ("xi", "xj", "yi", "yj", "z", "ai", "aj", "Wi", "Wj", "qij", "qji")  # struct admm_edge (u64 each)

@@ -203,7 +203,7 @@ class RayTransformCUDA:
     `op.colnorm2()` (= np.sum(A*A, axis=0), block_3_graph_and_precisions.py:22).
     """
 
-    def __init__(self, N, theta, D=None, det_w=2.0, device=0, impl="joseph"):
+    def __init__(self, N, theta, D=None, det_w=2.0, device=0, impl="joseph", angle_cell=None):
         if impl not in ("joseph", "astra_cuda", "astra_cpu", "skimage", None):
             raise ValueError(f"unknown impl {impl!r}")
         self.N = int(N)
@@ -215,7 +215,10 @@ class RayTransformCUDA:
         self.shape = (self.nang * self.D, self.N * self.N)
         h = 2.0 / self.N
         self.domain = DiscreteSpace((self.N, self.N), (h, h))
-        dth = math.pi / max(self.nang, 1)
+        # angular cell of the range space (it weights `.adjoint`): pi / m_k for a node that covers the whole half
+        # circle (`uniform_partition(0, pi, m_k)`, block_2_load_odl_data.py:51), pi / angles_total for a node that
+        # holds a contiguous block of the aggregate grid -- the caller passes it
+        dth = float(angle_cell) if angle_cell is not None else math.pi / max(self.nang, 1)
         self.range = DiscreteSpace((self.nang, self.D), (dth, self.det_w / self.D))
         self._plan = None
 
@@ -275,4 +278,4 @@ def stack_operators(ops):
     """Aggregate operator = vstack of node operators (block_2_load_odl_data.py:58-63 intent)."""
     N, D, det_w = ops[0].N, ops[0].D, ops[0].det_w
     theta = np.concatenate([o.theta for o in ops])
-    return RayTransformCUDA(N, theta, D, det_w, ops[0].device)
+    return RayTransformCUDA(N, theta, D, det_w, ops[0].device, angle_cell=ops[0].range.cell_sides[0])

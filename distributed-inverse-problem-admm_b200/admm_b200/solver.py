@@ -40,7 +40,7 @@ class ADMMEngine:
                  node_prec=None, tv_mu=None, tv_sweeps=1, cg_iters=8, phantom_true=None, weighted_z=False,
                  device=0, dist=None, rank=0, world=1, group=None, node_group=None, fuse_pupdate=True,
                  max_iters=200, ax_refresh_every=10, exchange="auto", exchange_phases=None, partition="auto",
-                 acceptance=False, max_tighten=2):
+                 acceptance=False, max_tighten=2, carry_residual=True):
         torch = _torch()
         nat.require_cuda()
         self.torch = torch
@@ -53,6 +53,7 @@ class ADMMEngine:
         self.S, self.C = int(tv_sweeps), int(cg_iters)
         # a14 accept / tighten-and-retry rule (block_6_admm_loop_ver2.py:100-176), decided on the device
         self.acceptance, self.max_tighten = bool(acceptance), int(max_tighten)
+        self.carry_r = bool(carry_residual)
         self.dist, self.rank, self.world, self.group = dist, int(rank), int(world), group
         self._G = G
         # NCCL exchange: posted in pieces, each right after the x-update of its block of nodes (hidden behind the next
@@ -392,6 +393,9 @@ class ADMMEngine:
         sref = ctypes.byref(st)
         # A x is carried by the CG recurrence (ax += alpha A p); it is re-projected every `ax_refresh_every` iterations
         st.reuse_ax = 0 if (self.k % self.ax_refresh_every == 0) else 1
+        # likewise the CG residual: the TV pass and the rhs0 assembly carry r = rhs0 + tvterm - H x along, so a solve
+        # starts without a back-projection; rebuilt from scratch on the refresh iterations
+        st.carry_r, st.reuse_r = (1, st.reuse_ax) if self.carry_r else (0, 0)
         nat.check(L.admm_rhs0(h, sref, self.nbr_ptr.data_ptr(), self.nbr_z.data_ptr(), self.nbr_y.data_ptr(),
                               self.nbr_q.data_ptr(), 0, self.V, self._stream()), "admm_rhs0")
         reqs = []
@@ -405,13 +409,13 @@ class ADMMEngine:
                     # :155-176 on the device: nodes whose |g| misses the target are solved again (warm start, masked
                     # launches), at most max_tighten times; no host round trip
                     nat.check(L.admm_accept(h, sref, n0, nn, eps_target, self.max_tighten, 1, self._stream()), "admm_accept")
-                    keep = st.reuse_ax
-                    st.masked, st.reuse_ax = 1, 1
+                    keep = (st.reuse_ax, st.reuse_r)
+                    st.masked, st.reuse_ax, st.reuse_r = 1, 1, st.carry_r
                     for _ in range(self.max_tighten):
                         nat.check(L.admm_x_update(h, sref, n0, nn, self.S, self.C, self._stream()), "admm_x_update")
                         nat.check(L.admm_accept(h, sref, n0, nn, eps_target, self.max_tighten, 0, self._stream()),
                                   "admm_accept")
-                    st.masked, st.reuse_ax = 0, keep
+                    st.masked, st.reuse_ax, st.reuse_r = 0, keep[0], keep[1]
             if self.phases > 1:
                 if ph == self.phases - 1 and getattr(self, "time_exchange", False):
                     self._ex_t0 = self.torch.cuda.Event(enable_timing=True)

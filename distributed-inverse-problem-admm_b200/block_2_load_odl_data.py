@@ -13,17 +13,21 @@ from admm_b200 import RayTransformCUDA, angle_split, default_angles_total, node_
 from Gen_Sino_Partitioned import ConstIm, randIm  # noqa: F401
 
 
-def _build_parallel_beam_operators(N, num_nodes, angles_total=None, det_width_factor=1.0, partition="contiguous",
+def _build_parallel_beam_operators(N, num_nodes, angles_total=None, det_width_factor=1.0, partition="reference_literal",
                                    device=0):
     """block_2_load_odl_data.py:16-65.  Image space [-1,1]^2, N x N, float32 (:23-28); angles_total default
     max(180, 3N) (:31-33); integer split (:36-38); detector width det_width_factor*2 with N bins (:42-44).
-    `partition`: see admm_b200.geometry.node_angles."""
+    `partition`: "reference_literal" (default) is what the shipped code does -- every node gets the
+    midpoints of uniform_partition(0, pi, m_k) (:51), the aggregate its own pi/angles_total grid (:59-63);
+    "contiguous" gives node k the k-th block of the aggregate grid (north_star's angle-partitioned operators, what
+    bench.py times; then the aggregate is the vstack of the nodes)."""
     if angles_total is None:
         angles_total = default_angles_total(N)
     det_width = det_width_factor * 2.0
     thetas = node_angles(angles_total, num_nodes, partition)
     assert [len(t) for t in thetas] == angle_split(angles_total, num_nodes)
-    ray_transforms = [RayTransformCUDA(N, t, D=N, det_w=det_width, device=device) for t in thetas]
+    cell = np.pi / angles_total if partition == "contiguous" else None       # else pi / m_k (RayTransformCUDA default)
+    ray_transforms = [RayTransformCUDA(N, t, D=N, det_w=det_width, device=device, angle_cell=cell) for t in thetas]
     if partition == "contiguous":
         agg = stack_operators(ray_transforms)
     else:
@@ -35,7 +39,7 @@ def _build_parallel_beam_operators(N, num_nodes, angles_total=None, det_width_fa
 def load_odl_data(base_dir="saved_operators_Incmp_Span", N=64, num_nodes=5, noise_level=0.005, phantom_array=None,
                   ray_transforms_pickle=None, A_dense_list_pickle=None, agg_op_pickle=None, A_agg_pickle=None,
                   make_plots=False, show_plots=False, output_dir=None, save_operators_dir=None, build_dense=False,
-                  angles_total=None, partition="contiguous", seed=None, device=0):
+                  angles_total=None, partition="reference_literal", seed=None, device=0):
     """Union of both reference signatures (block_2_test.py:15-26, block_2_load_odl_data.py:99-109).
 
     Sinograms: b_i = A_i x + noise_level * N(0, 1) (block_2_load_odl_data.py:148-154 / block_2_test.py:54-60), drawn

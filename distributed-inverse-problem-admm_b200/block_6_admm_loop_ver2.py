@@ -49,7 +49,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                        cg_iters=8, tv_sweeps=1, tv_mu=None, node_prec=None, weighted_z=False, scs_eps=None,
                        check_every=1, node_group=None, fuse_pupdate=True, device=None, return_engine=False,
                        distributed=None, ax_refresh_every=10, exchange="auto", gather="all", exchange_phases=None, partition="auto",
-                       acceptance=True, max_tighten=2,
+                       acceptance=True, max_tighten=2, carry_residual=True,
                        **kwargs):
     """Returns x_per_node as list of reconstructions, each length n, and the history of residual norms
     (block_6_admm_loop_ver2.py:21-24).
@@ -105,7 +105,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                      weighted_z=weighted_z, device=device, dist=dist if world > 1 else None, rank=rank, world=world,
                      group=group, node_group=node_group, fuse_pupdate=fuse_pupdate, max_iters=max_iters,
                      ax_refresh_every=ax_refresh_every, exchange=exchange, exchange_phases=exchange_phases, partition=partition,
-                     acceptance=acceptance, max_tighten=max_tighten)
+                     acceptance=acceptance, max_tighten=max_tighten, carry_residual=carry_residual)
     eng._node_prec_all = node_prec
 
     def _solve_and_collect():

@@ -251,7 +251,7 @@ extern "C" long long admm_plan_info(const admm_plan* p, int what) {
         case ADMM_INFO_PART_FLOATS: {
             const long long tiles = (long long)((p->N + 31) / 32) * ((p->N + 31) / 32);       // back-projector grid
             const long long tvblk = (long long)((p->N + 127) / 128) * ((p->N + 7) / 8);       // TV grid
-            return std::max(std::max(3 * tiles, 3 * tvblk), 5LL * 4096);
+            return std::max(std::max(3 * tiles, 4 * tvblk), 5LL * 4096);
         }
         case ADMM_INFO_FWD_SPAN: return p->span;
         case ADMM_INFO_FWD_NREC: return (long long)p->nTi * p->nSeg;
@@ -376,6 +376,11 @@ extern "C" int admm_rhs0(admm_plan* p, const admm_state* s, const int* d_nbr_ptr
     R.atb = s->atb + off; R.rhs0 = s->rhs0 + off; R.nbr_ptr = d_nbr_ptr; R.nbr_z = d_nbr_z; R.nbr_y = d_nbr_y;
     R.nbr_q = d_nbr_q; R.stride = s->stride; R.n = (long long)p->N * p->N; R.node0 = node0; R.rho = s->rho;
     R.q_uniform = s->q_uniform;
+    if (s->carry_r && s->reuse_r) {   // the residual rides along: r += rhs0' - rhs0 ; p0 = r ; <r,r> -> S_RR0
+        R.r_upd = s->r + off; R.p_out = s->p0 + off;
+        R.part = s->part + (long long)node0 * admm_plan_info(p, ADMM_INFO_PART_FLOATS);
+        R.counter = s->counter + node0; R.scal = s->scal;
+    }
     CK(launch_rhs0(R, nodes, (cudaStream_t)stream));
     return ADMM_OK;
 }
@@ -387,7 +392,8 @@ static TvParams make_tv(const admm_plan* p, const admm_state* s, int node0, bool
     const float* win = parity ? s->w1 : s->w0;
     float* wout = parity ? s->w0 : s->w1;
     T.x = s->x + off; T.w_in = win + 2 * off; T.w_out = wout + 2 * off; T.tvterm = s->tvterm + off;
-    T.r = diag ? s->r + off : nullptr; T.xtrue = s->xtrue; T.stride = s->stride; T.node0 = node0; T.N = p->N;
+    T.r = diag ? s->r + off : nullptr; T.xtrue = s->xtrue;
+    if (s->carry_r) { T.r_upd = s->r + off; T.p_out = s->p0 + off; } T.stride = s->stride; T.node0 = node0; T.N = p->N;
     T.lam = s->lam; T.mu = s->mu;
     T.part = s->part + (long long)node0 * admm_plan_info(p, ADMM_INFO_PART_FLOATS);
     T.counter = s->counter + node0; T.scal = s->scal;
@@ -432,7 +438,9 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
         B.v = s->x + off; B.rhoD_vec = s->rhoD_vec ? s->rhoD_vec + off : nullptr; B.rhoD_s = s->rhoD_s; B.mu = s->mu;
         B.rhs0 = s->rhs0 + off; B.tvterm = s->tvterm + off; B.p_out = s->p0 + off;
         B.part = part; B.counter = counter; B.scal = s->scal; B.dot_slot = S_RR0; B.ctl = mask;
-        CK(launch_back(BACK_RESID0, B, nodes, st));
+        // with carry_r the TV pass (r += tvterm' - tvterm) and the rhs0 assembly (r += rhs0' - rhs0) keep r = rhs0 +
+        // tvterm - H x, p0 = r and <r,r> current, so the solve starts without this back-projection
+        if (!(s->carry_r && (sw > 0 || s->reuse_r))) CK(launch_back(BACK_RESID0, B, nodes, st));
         int cur = 0;
         float* rcur = s->r + off;            // residual buffer currently holding r (fuse 2 ping-pongs r / r1)
         for (int it = 0; it < cg_iters; ++it) {

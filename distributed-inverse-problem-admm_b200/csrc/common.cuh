@@ -80,9 +80,11 @@ __device__ __forceinline__ void block_sum(float (&v)[K], float* red) {
 //   part:    [nblk][K] floats for this group;  counter: one unsigned for this group.
 // Must be called by all threads of the block; v[] valid in thread 0 (output of block_sum).
 // Returns true in every thread of the last block (after the result is stored), false elsewhere.
+// `slots` (optional): out[slots[k]] receives value k instead of out[k].
 template <int K>
 __device__ __forceinline__ bool grid_reduce_store(const float (&v)[K], float* part, unsigned* counter,
-                                                  int blk, int nblk, double* out, float* red) {
+                                                  int blk, int nblk, double* out, float* red,
+                                                  const int* slots = nullptr) {
     __shared__ int s_last;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
     if (tid == 0) {
@@ -116,7 +118,7 @@ __device__ __forceinline__ bool grid_reduce_store(const float (&v)[K], float* pa
             if (tid == 0) {
                 double s = 0.0;
                 for (int w = 0; w < nw; ++w) s += dred[w];
-                out[k] = s;
+                out[slots ? slots[k] : k] = s;
             }
         }
         if (tid == 0) *counter = 0u;

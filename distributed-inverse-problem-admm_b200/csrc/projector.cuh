@@ -102,7 +102,8 @@ enum ScalSlot : int {
     S_TV = 5,               // canonical TV(x)
     S_GN2 = 6,              // |g|^2 stationarity
     S_IMG = 7,              // |x - x_true|^2
-    S_MSE = 8               // |Ax - b|^2
+    S_MSE = 8,              // |Ax - b|^2
+    S_SCRATCH = 15          // sink for reductions whose result is not wanted
 };
 
 }  // namespace admm

@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_seg(const float* __restrict__ row, int c, i
 
 __global__ void __launch_bounds__(TVX * TVY, 4)
 tv_fused_kernel(const TvParams P) {
-    __shared__ __align__(16) float red[96];
+    __shared__ __align__(16) float red[128];
     const int N = P.N;
     const int node = P.node0 + blockIdx.z;
     if (P.masked && !P.ctl[node].active) return;   // a14 retry pass: this node was accepted already
@@ -72,7 +72,7 @@ tv_fused_kernel(const TvParams P) {
     float* __restrict__ wo1 = (swap ? const_cast<float*>(P.w_in) : P.w_out) + 2 * nb;
     float* __restrict__ wo2 = wo1 + n;
     const float kappa = P.lam / P.mu;
-    float tv = 0.f, gn2 = 0.f, img = 0.f;
+    float tv = 0.f, gn2 = 0.f, img = 0.f, rr = 0.f;
     if (r < N && c0 < N) {
         const bool vec = ((N & 3) == 0);   // then c0 + 3 < N and rows are 16-byte aligned
         const long long g0 = (long long)r * N + c0;
@@ -129,18 +129,20 @@ tv_fused_kernel(const TvParams P) {
         float w1o[4], w2o[4], tvo[4];
         float told[4], rc[4], xt[4];
         const bool diag = (P.r != nullptr);
+        const bool upd = (P.r_upd != nullptr);
+        const float* rsrc = upd ? P.r_upd : P.r;
         float* __restrict__ tvt = P.tvterm + nb;
         if (vec) {
             const float4 t4 = ld4(tvt + g0);
             told[0] = t4.x; told[1] = t4.y; told[2] = t4.z; told[3] = t4.w;
-            if (diag) { const float4 q = ld4(P.r + nb + g0); rc[0] = q.x; rc[1] = q.y; rc[2] = q.z; rc[3] = q.w; }
+            if (diag || upd) { const float4 q = ld4(rsrc + nb + g0); rc[0] = q.x; rc[1] = q.y; rc[2] = q.z; rc[3] = q.w; }
             if (P.xtrue) { const float4 q = ld4(P.xtrue + g0); xt[0] = q.x; xt[1] = q.y; xt[2] = q.z; xt[3] = q.w; }
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const bool ok = c0 + k < N;
                 told[k] = ok ? tvt[g0 + k] : 0.f;
-                rc[k] = (ok && diag) ? P.r[nb + g0 + k] : 0.f;
+                rc[k] = (ok && (diag || upd)) ? rsrc[nb + g0 + k] : 0.f;
                 xt[k] = (ok && P.xtrue) ? P.xtrue[g0 + k] : 0.f;
             }
         }
@@ -186,21 +188,40 @@ tv_fused_kernel(const TvParams P) {
             w1o[k] = o.w1; w2o[k] = o.w2; tvo[k] = P.mu * kt;
             dwy_prev = o.dwy; py_prev = pyo;
         }
+        float rn[4];   // residual of the NEXT solve: r + (tvterm' - tvterm)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            rn[k] = rc[k] + (tvo[k] - told[k]);
+            if (upd && c0 + k < N) rr = fmaf(rn[k], rn[k], rr);
+        }
         if (vec) {
             st4(wo1 + g0, make_float4(w1o[0], w1o[1], w1o[2], w1o[3]));
             st4(wo2 + g0, make_float4(w2o[0], w2o[1], w2o[2], w2o[3]));
             st4(tvt + g0, make_float4(tvo[0], tvo[1], tvo[2], tvo[3]));
+            if (upd) {
+                st4(P.r_upd + nb + g0, make_float4(rn[0], rn[1], rn[2], rn[3]));
+                st4(P.p_out + nb + g0, make_float4(rn[0], rn[1], rn[2], rn[3]));
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (c0 + k < N) { wo1[g0 + k] = w1o[k]; wo2[g0 + k] = w2o[k]; tvt[g0 + k] = tvo[k]; }
+                if (c0 + k < N) {
+                    wo1[g0 + k] = w1o[k]; wo2[g0 + k] = w2o[k]; tvt[g0 + k] = tvo[k];
+                    if (upd) { P.r_upd[nb + g0 + k] = rn[k]; P.p_out[nb + g0 + k] = rn[k]; }
+                }
         }
     }
-    float v[3] = {tv, gn2, img};
-    block_sum<3>(v, red);
+    float v[4] = {tv, gn2, img, rr};
+    block_sum<4>(v, red);
     const int nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
-    const bool last = grid_reduce_store<3>(v, P.part + (long long)blockIdx.z * nblk * 3, P.counter + blockIdx.z, blk,
-                                           nblk, P.scal + (long long)node * NSCAL + S_TV, red);
+    __shared__ int s_slots[4];
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        s_slots[0] = S_TV; s_slots[1] = S_GN2; s_slots[2] = S_IMG;
+        s_slots[3] = P.r_upd ? S_RR0 : S_SCRATCH;
+    }
+    // (s_slots is ordered before its use by the barriers inside grid_reduce_store)
+    const bool last = grid_reduce_store<4>(v, P.part + (long long)blockIdx.z * nblk * 4, P.counter + blockIdx.z, blk,
+                                           nblk, P.scal + (long long)node * NSCAL, red, s_slots);
     if (last && P.ctl && threadIdx.x == 0 && threadIdx.y == 0) P.ctl[node].wpar ^= 1;
 }
 
@@ -312,11 +333,16 @@ sino_resid_kernel(const SinoParams P) {
 // =================================================================================================
 __global__ void __launch_bounds__(256)
 rhs0_kernel(const RhsParams P) {
+    __shared__ __align__(16) float red[32];
     const int node = P.node0 + blockIdx.y;
     const long long nb = (long long)blockIdx.y * P.stride;
     const int kb = P.nbr_ptr[node], ke = P.nbr_ptr[node + 1];
     const float* __restrict__ atb = P.atb + nb;
-    float* __restrict__ out = P.rhs0 + nb;
+    float* out = P.rhs0 + nb;
+    const bool upd = (P.r_upd != nullptr);
+    float* rio = upd ? P.r_upd + nb : nullptr;
+    float* po = upd ? P.p_out + nb : nullptr;
+    float rr = 0.f;
     const long long n4 = ((P.n & 3) == 0 && (P.stride & 3) == 0) ? (P.n >> 2) : 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 cons = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -330,7 +356,15 @@ rhs0_kernel(const RhsParams P) {
             cons.z += P.rho * qv.z * (z.z - y.z); cons.w += P.rho * qv.w * (z.w - y.w);
         }
         const float4 a = ld4(atb + 4 * i);
-        st4(out + 4 * i, make_float4(a.x + cons.x, a.y + cons.y, a.z + cons.z, a.w + cons.w));
+        const float4 nw = make_float4(a.x + cons.x, a.y + cons.y, a.z + cons.z, a.w + cons.w);
+        if (upd) {
+            const float4 od = ld4(out + 4 * i), rv = ld4(rio + 4 * i);
+            const float4 rn = make_float4(rv.x + (nw.x - od.x), rv.y + (nw.y - od.y), rv.z + (nw.z - od.z), rv.w + (nw.w - od.w));
+            st4(rio + 4 * i, rn);
+            st4(po + 4 * i, rn);
+            rr = fmaf(rn.x, rn.x, rr); rr = fmaf(rn.y, rn.y, rr); rr = fmaf(rn.z, rn.z, rr); rr = fmaf(rn.w, rn.w, rr);
+        }
+        st4(out + 4 * i, nw);
     }
     for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += (long long)gridDim.x * blockDim.x) {
         float cons = 0.f;
@@ -341,7 +375,18 @@ rhs0_kernel(const RhsParams P) {
             const float qv = q ? q[i] : P.q_uniform;
             cons += P.rho * qv * (z[i] - y[i]);
         }
-        out[i] = atb[i] + cons;
+        const float nw = atb[i] + cons;
+        if (upd) {
+            const float rn = rio[i] + (nw - out[i]);
+            rio[i] = rn; po[i] = rn; rr = fmaf(rn, rn, rr);
+        }
+        out[i] = nw;
+    }
+    if (upd) {   // launch-uniform
+        float v[1] = {rr};
+        block_sum<1>(v, red);
+        grid_reduce_store<1>(v, P.part + (long long)blockIdx.y * gridDim.x, P.counter + blockIdx.y, blockIdx.x, gridDim.x,
+                             P.scal + (long long)node * NSCAL + S_RR0, red);
     }
 }
 

@@ -10,6 +10,9 @@ struct TvParams {
     float* w_out;          // [nodes][2][n] (new; must not alias w_in)
     float* tvterm;         // [nodes][n] in: mu K^T(d-w) used by the last solve; out: the new one
     const float* r;        // [nodes][n] final CG residual (nullptr: skip the stationarity diagnostic)
+    float* r_upd;          // [nodes][n] or nullptr: carry the residual to the next solve without a back-projection --
+                           //   r += tvterm' - tvterm ; p_out = r ; <r,r> -> scal[S_RR0]   (r = rhs0 + tvterm - H x stays true)
+    float* p_out;          // [nodes][n] CG start direction (with r_upd)
     const float* xtrue;    // [n] or nullptr
     long long stride;
     int node0, N;
@@ -52,6 +55,10 @@ struct RhsParams {
     long long stride, n;
     int node0;
     float rho, q_uniform;
+    // optional (r_upd != nullptr): carry the CG residual across the outer iteration, r += rhs0' - rhs0 ; p_out = r ;
+    // <r,r> -> scal[S_RR0], so the next solve starts without the A^T(P A x) back-projection of its residual
+    float* r_upd; float* p_out;
+    float* part; unsigned* counter; double* scal;
 };
 
 struct EdgeDesc {

@@ -77,6 +77,11 @@ typedef struct admm_state {
     struct admm_node_ctl* ctl; /* [V] per-node control words of the a14 accept / tighten rule, or NULL.  When set, the
                                  TV-multiplier parity is per node and device-resident (w_parity is ignored)   */
     int masked;               /* 1: admm_x_update / admm_tv_pass skip the nodes whose ctl[].active is 0 (retry pass) */
+    int carry_r;              /* 1: the TV pass also carries the CG residual to the next solve (r += tvterm' - tvterm,
+                                 p0 = r, <r,r>), and so does admm_rhs0 when reuse_r is set (r += rhs0' - rhs0): a solve
+                                 then starts without the A^T(P A x) back-projection of its residual                  */
+    int reuse_r;              /* 1: r, p0 and <r,r> are current for the solve that follows (set 0 periodically, and for
+                                 the first solve, to rebuild r = rhs0 + tvterm - H x and stop fp32 drift)             */
 } admm_state;
 
 /* Per-node control word (block_6_admm_loop_ver2.py:110-113 `accepted`, `tighten_tries`): zero-initialised by the

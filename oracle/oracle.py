@@ -508,7 +508,7 @@ def np_x_update(op, prec, rhs0, rhoD, mu, lam, S, C, x, d, w):
 def decentralized_admm(ops, sinograms, G, Wi_list, Qij_diag_fn, N, lam_tv=0.01, rho=1.0, max_iters=10,
                        eps_pri=1e-1, eps_dual=1e-1, phantom_true=None, node_prec=None, tv_mu=None,
                        tv_sweeps=1, cg_iters=8, weighted_z=False, uniform_q=None, stop=True,
-                       x_update_fn=None, node_subset=None, acceptance=True, max_tighten=2):
+                       x_update_fn=None, node_subset=None, acceptance=True, max_tighten=2, on_iteration=None):
     """Array restatement of block_6_admm_loop_ver2.py:15-326 with the SCS solve (:97-176) replaced by the
     TV-split + CG x-update.  Same initialisation (:36-46), Jacobi node sweep (:81-97,187), metrics (:189-206),
     midpoint z (:210-223) [W-weighted PDF eq. (2) if ``weighted_z``], duals (:225-230), residuals (:232-264),
@@ -637,6 +637,8 @@ def decentralized_admm(ops, sinograms, G, Wi_list, Qij_diag_fn, N, lam_tv=0.01, 
         hist["obj_total"].append(float(np.sum(obj_i)))
         hist["pri_per_node"].append(np.sqrt(pri_node))
         hist["dual_per_node"].append(np.sqrt(dual_node))
+        if on_iteration is not None:
+            on_iteration(k, x)
         if stop and pri_norm < eps_pri and dual_norm < eps_dual:
             break
     return x, hist

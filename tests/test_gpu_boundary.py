@@ -40,22 +40,35 @@ def test_block2_block3_gen_sino_against_oracle():
     import Gen_Sino_Partitioned as gs
     from oracle import oracle as O
     N, V = 64, 5
-    data = b2.load_odl_data(N=N, num_nodes=V, noise_level=0.0, phantom_array=gs.ConstIm(N), make_plots=False)
-    for key in ("A_dense_list", "sinograms", "column_norms_all", "N", "num_nodes", "agg_ray_trafo", "A_agg",
-                "agg_sinogram", "agg_fbp_recon", "agg_ls_recon", "output_dir", "phantom", "phantoms"):
-        assert key in data
     M = max(180, 3 * N)                                    # block_2_load_odl_data.py:31-33
     per = O.angle_split(M, V)
-    thetas = O.node_angles(M, V)
-    assert [A.shape for A in data["A_dense_list"]] == [(m * N, N * N) for m in per]
-    for i in range(V):
-        ref = O.JosephOperator(N, thetas[i])
-        assert data["sinograms"][i].shape == (per[i], N)
-        assert _rel(data["sinograms"][i], ref.forward(gs.ConstIm(N))) < 1e-4
-        assert _rel(data["column_norms_all"][i], np.sqrt(ref.colnorm2())) < 1e-4
-    # aggregate operator == vstack of the node operators (contiguous partition)
-    agg = data["agg_ray_trafo"](data["agg_ray_trafo"].domain.element(gs.ConstIm(N))).asarray()
-    assert _rel(agg, np.vstack(data["sinograms"])) < 1e-6
+    for part in ("reference_literal", "contiguous"):
+        # default = what the shipped code builds (block_2_load_odl_data.py:51)
+        kwp = {} if part == "reference_literal" else {"partition": part}
+        data = b2.load_odl_data(N=N, num_nodes=V, noise_level=0.0, phantom_array=gs.ConstIm(N), make_plots=False, **kwp)
+        for key in ("A_dense_list", "sinograms", "column_norms_all", "N", "num_nodes", "agg_ray_trafo", "A_agg",
+                    "agg_sinogram", "agg_fbp_recon", "agg_ls_recon", "output_dir", "phantom", "phantoms"):
+            assert key in data
+        thetas = O.node_angles(M, V, part)
+        assert [A.shape for A in data["A_dense_list"]] == [(m * N, N * N) for m in per]
+        for i in range(V):
+            ref = O.JosephOperator(N, thetas[i])
+            assert data["sinograms"][i].shape == (per[i], N)
+            assert _rel(data["sinograms"][i], ref.forward(gs.ConstIm(N))) < 1e-4
+            assert _rel(data["column_norms_all"][i], np.sqrt(ref.colnorm2())) < 1e-4
+            # ODL-weighted adjoint (w_Y / w_X) A^T with the node's TRUE angular cell: pi/m_k on the literal grids,
+            # pi/angles_total for a contiguous block
+            op = data["A_dense_list"][i]
+            cell = np.pi / per[i] if part == "reference_literal" else np.pi / M
+            assert abs(op.range.cell_sides[0] - cell) < 1e-15
+            q = np.random.default_rng(i).standard_normal(op.range.shape)
+            want = (cell * (2.0 / N)) / (2.0 / N) ** 2 * ref.adjoint(q.reshape(-1))
+            assert _rel(op.adjoint(op.range.element(q)).asarray().reshape(-1), want) < 1e-4
+        agg = data["agg_ray_trafo"](data["agg_ray_trafo"].domain.element(gs.ConstIm(N))).asarray()
+        assert agg.shape == (M, N)
+        if part == "contiguous":   # aggregate operator == vstack of the node operators
+            assert _rel(agg, np.vstack(data["sinograms"])) < 1e-6
+            assert abs(data["agg_ray_trafo"].range.cell_sides[0] - np.pi / M) < 1e-15
     # block_3 on operators
     Wi, Q = b3.make_precisions(data["A_dense_list"], q_mode="harmonic")
     Wo, Qo = O.make_precisions([O.JosephOperator(N, t).colnorm2() for t in thetas], "harmonic")

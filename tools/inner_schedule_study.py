@@ -51,6 +51,16 @@ SCHEDULES = [
     ("S2C4 mu=4rho", 2, 4, False, 4 * RHO),
     ("S4C2 mu=4rho", 4, 2, False, 4 * RHO),
     ("S8C4 mu=4rho", 8, 4, False, 4 * RHO),
+    # what decides the accuracy is the number of TV sweeps, not the CG count: cheap sweeps
+    ("S1C1+accept", 1, 1, True, RHO),
+    ("S1C2+accept", 1, 2, True, RHO),
+    ("S2C2+accept", 2, 2, True, RHO),
+    ("S2C1+accept", 2, 1, True, RHO),
+    ("S4C1", 4, 1, False, RHO),
+    ("S6C1", 6, 1, False, RHO),
+    ("S6C2", 6, 2, False, RHO),
+    ("S8C1", 8, 1, False, RHO),
+    ("S12C2", 12, 2, False, RHO),
 ]
 
 
