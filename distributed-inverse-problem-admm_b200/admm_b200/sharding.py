@@ -71,14 +71,24 @@ def _map_score(edges, nr, world):
     return (max(per) if per else 0, cut)
 
 
-def partition_nodes(G, world: int, method: str = "auto", trials: int = 16, seed: int = 1234) -> list:
+def partition_nodes(G, world: int, method: str = "auto", trials: int = 16, seed: int = 1234, weights=None) -> list:
     """Node -> GPU map with V//world or V//world+1 nodes per rank (the x-update work is per node, so the map stays
     balanced).  "contiguous": gpu(i) = (i*G)//V (SURVEY 8(e)).  "mincut": deterministic multi-start pairwise-swap
     refinement (Kernighan-Lin moves on the cut size, vectorised: gain(i,j) = P[i,part j] + P[j,part i] - 2 A[i,j]
     with P[i,w] = #nbrs of i in w - #nbrs of i in its own part), best of `trials` starts by (max cut-edge ends on a
     rank, cut edges); never worse than contiguous, which is start 0.  "auto": mincut for V <= 256, else contiguous
     (the search is O(V^2) per move; slice-batched graphs are disjoint unions that the contiguous map already keeps
-    whole).  Every rank calls this with the same arguments and gets the same list."""
+    whole).  Every rank calls this with the same arguments and gets the same list.
+
+    `weights` (one integer per node, e.g. its number of projection angles -- the projector kernels' time is
+    proportional to the angle rows a rank holds): the map is then also balanced by weight.  Definition, so that it can
+    be re-derived: nodes are sorted by (-weight, id) and dealt to the ranks in snake order (0..G-1, G-1..0, ...):
+    every rank gets V//G or V//G+1 nodes and the rank weights differ by at most max(weights) - min(weights); that is
+    start 0.  Start t > 0 permutes, with np.random.RandomState(seed) drawn once for all starts in order, the nodes
+    WITHIN each weight class before dealing.  Each start is refined by the swap moves above restricted to pairs of
+    EQUAL weight (rank weights never change), ties in the gain broken by the smallest flat index i*V + j; the best
+    start by (max cut-edge ends on a rank, cut edges, start index) wins; ranks are relabelled in order of their
+    smallest node id."""
     V = G.number_of_nodes()
     cont = node_to_gpu(V, world)
     if method not in ("auto", "mincut", "contiguous"):
@@ -88,10 +98,17 @@ def partition_nodes(G, world: int, method: str = "auto", trials: int = 16, seed:
     edges = graph_csr(G)[0]
     if len(edges) == 0:
         return cont
-    key = (V, world, trials, seed, edges.tobytes())
+    w = None
+    if weights is not None:
+        w = np.asarray([int(v) for v in weights], dtype=np.int64)
+        if len(w) != V:
+            raise ValueError("weights must hold one value per node")
+        if np.all(w == w[0]):
+            w = None                                  # uniform: the plain balanced min-cut
+    key = (V, world, trials, seed, edges.tobytes(), None if w is None else w.tobytes())
     if key in _PARTITION_CACHE:                       # repeated solves on one graph (e.g. bench.py's two legs)
         return list(_PARTITION_CACHE[key])
-    result = _mincut_partition(edges, V, world, cont, trials, seed)
+    result = _mincut_partition(edges, V, world, cont, trials, seed, w)
     if len(_PARTITION_CACHE) < 64:
         _PARTITION_CACHE[key] = tuple(result)
     return result
@@ -100,17 +117,42 @@ def partition_nodes(G, world: int, method: str = "auto", trials: int = 16, seed:
 _PARTITION_CACHE: dict = {}
 
 
-def _mincut_partition(edges, V, world, cont, trials, seed) -> list:
+def _snake_deal(order, V, world):
+    part = np.zeros(V, dtype=np.int64)
+    for k, g in enumerate(order):
+        r, c = divmod(k, world)
+        part[g] = c if r % 2 == 0 else world - 1 - c
+    return part
+
+
+def _mincut_partition(edges, V, world, cont, trials, seed, w=None) -> list:
     A = np.zeros((V, V), dtype=np.int32)
     for i, j in edges:
         A[int(i), int(j)] = A[int(j), int(i)] = 1
     rng = np.random.RandomState(seed)
-    best, best_score = cont, _map_score(edges, cont, world)
+    if w is None:
+        best, best_score = cont, _map_score(edges, cont, world)
+        same_w = None
+    else:
+        best, best_score = None, None
+        same_w = w[:, None] == w[None, :]
     rows = np.arange(V)
     for t in range(max(1, trials)):
-        part = np.asarray(cont, dtype=np.int64)
-        if t > 0:
-            part = part[rng.permutation(V)]
+        if w is None:
+            part = np.asarray(cont, dtype=np.int64)
+            if t > 0:
+                part = part[rng.permutation(V)]
+        else:
+            order = sorted(range(V), key=lambda g: (-int(w[g]), g))
+            if t > 0:                                  # shuffle inside each weight class
+                keyed = {}
+                for g in order:
+                    keyed.setdefault(int(w[g]), []).append(g)
+                order = []
+                for wt in sorted(keyed, reverse=True):
+                    cls = keyed[wt]
+                    order += [cls[k] for k in rng.permutation(len(cls))]
+            part = _snake_deal(order, V, world)
         for _ in range(8 * V):
             X = np.zeros((V, world), dtype=np.int32)
             X[rows, part] = 1
@@ -119,6 +161,8 @@ def _mincut_partition(edges, V, world, cont, trials, seed) -> list:
             M = P[:, part]                              # M[i, j] = P[i, part(j)]
             gain = M + M.T - 2 * A
             gain[part[:, None] == part[None, :]] = -1
+            if same_w is not None:
+                gain[~same_w] = -1                      # only swaps that leave every rank's weight unchanged
             k = int(np.argmax(gain))
             i, j = divmod(k, V)
             if gain[i, j] <= 0:
@@ -130,7 +174,7 @@ def _mincut_partition(edges, V, world, cont, trials, seed) -> list:
             order.setdefault(int(part[g]), len(order))
         cand = [order[int(part[g])] for g in range(V)]
         sc = _map_score(edges, cand, world)
-        if sc < best_score:
+        if best_score is None or sc < best_score:
             best, best_score = cand, sc
     return best
 

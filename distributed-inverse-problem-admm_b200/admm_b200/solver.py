@@ -37,10 +37,10 @@ class ADMMEngine:
     """
 
     def __init__(self, thetas, sinograms, G, N, D=None, det_w=2.0, lam_tv=0.01, rho=1.0, Q=None, Wi_list=None,
-                 node_prec=None, tv_mu=None, tv_sweeps=1, cg_iters=8, phantom_true=None, weighted_z=False,
+                 node_prec=None, tv_mu=None, tv_sweeps=1, cg_iters=2, phantom_true=None, weighted_z=False,
                  device=0, dist=None, rank=0, world=1, group=None, node_group=None, fuse_pupdate=True,
                  max_iters=200, ax_refresh_every=10, exchange="auto", exchange_phases=None, partition="auto",
-                 acceptance=False, max_tighten=2, carry_residual=True):
+                 acceptance=False, max_tighten=2, carry_residual=False):
         torch = _torch()
         nat.require_cuda()
         self.torch = torch
@@ -68,8 +68,9 @@ class ADMMEngine:
         if self.world > G.number_of_nodes():
             # every rank sees the same graph, so every rank raises here -- before any collective can hang
             raise ValueError(f"{self.world} ranks but only {G.number_of_nodes()} graph nodes: a rank would own no node")
-        self.node_rank = (partition_nodes(G, self.world, partition) if isinstance(partition, str)
-                          else [int(r) for r in partition])
+        # (balanced by node count AND by angle rows: the projector kernels' time follows the angles a rank holds)
+        self.node_rank = (partition_nodes(G, self.world, partition, weights=[len(t) for t in thetas])
+                          if isinstance(partition, str) else [int(r) for r in partition])
         self.sp: ShardPlan = build_shard_plan(G, self.world, self.rank, self.phases, self.node_rank)
         sp = self.sp
         self.Vg = sp.V
@@ -467,9 +468,12 @@ class ADMMEngine:
         if self.exchange_mode == "p2p":
             if self._side is not None:
                 self.torch.cuda.current_stream().wait_event(self._pushed)
-            # device-side barrier: every rank's pack of this iteration has completed before anyone reads it; the
-            # double buffer makes this the only synchronisation the exchange needs
-            self.dist.all_reduce(self._bar, group=self.group)
+            # device-side barrier: every rank's pack of this iteration has completed before anyone reads it (the double
+            # buffer makes this the only synchronisation the exchange needs).  The barrier IS the all-reduce of the
+            # previous iteration's residual row, which nothing on the device needs any earlier: ONE collective per
+            # iteration instead of two (a dedicated one-float all-reduce only when no row is pending)
+            if not self._flush_row():
+                self.dist.all_reduce(self._bar, group=self.group)
         for r in reqs:
             r.wait()          # stream-level wait: the compute stream now depends on the received buffers
         if getattr(self, "_edges_timed", None):
@@ -485,13 +489,27 @@ class ADMMEngine:
                                   self.edge_fl.data_ptr(), self.E, self.n_edges_local, self.node_gid.data_ptr(),
                                   self.fin_ptr.data_ptr(), self.fin_epos.data_ptr(), self.fin_end.data_ptr(), self.Vg,
                                   self.row.data_ptr(), self._stream()), "admm_finalize")
-        if self.world > 1:
-            self.dist.all_reduce(self.row, group=self.group)  # the only data collective
         if self.k >= self.hist.shape[0]:      # engine re-used past its first max_iters: grow the history buffer
             grown = self.torch.zeros(2 * self.hist.shape[0], self.ROW, dtype=self.torch.float64, device=self.dev)
             grown[: self.hist.shape[0]] = self.hist
             self.hist = grown
         self.hist[self.k].copy_(self.row)
+        if self.world > 1:
+            # the only data collective: the sum of the ranks' rows.  Peer-memory exchange: deferred to the
+            # next iteration's barrier (or to whoever reads the residuals first); NCCL exchange: right away
+            self._pending_row = self.k
+            if self.exchange_mode != "p2p":
+                self._flush_row()
+
+    def _flush_row(self):
+        """All-reduce the residual row of the last finished iteration in place in the history (collective: every rank
+        reaches it at the same point of the same loop).  Returns False when nothing was pending."""
+        k = getattr(self, "_pending_row", None)
+        if k is None or self.world == 1:
+            return False
+        self.dist.all_reduce(self.hist[k], group=self.group)
+        self._pending_row = None
+        return True
 
     def step(self):
         reqs = self.nodes_phase()
@@ -512,11 +530,13 @@ class ADMMEngine:
     # ---- results --------------------------------------------------------------------------------------------
     def residuals(self):
         """(primal, dual) norms of the last completed iteration -- forces a device sync."""
-        r = self.row[:2].cpu().numpy()
+        self._flush_row()
+        r = self.hist[self.k - 1, :2].cpu().numpy() if self.k > 0 else np.zeros(2)
         return math.sqrt(r[0]), math.sqrt(r[1])
 
     def history(self, iters=None):
         """History dict with the keys of block_6_admm_loop_ver2.py:310-326 (one entry per iteration)."""
+        self._flush_row()
         iters = self.k if iters is None else min(int(iters), self.k)
         H = self.hist[:iters].cpu().numpy()
         Vg = self.Vg

@@ -46,16 +46,18 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                        verbose=True, snapshot_dir=None,
                        snapshot_every=None, snapshot_div=10, phantom_true=None,
                        # --- B200 solver controls (not in the reference) ---
-                       cg_iters=8, tv_sweeps=1, tv_mu=None, node_prec=None, weighted_z=False, scs_eps=None,
+                       cg_iters=2, tv_sweeps=1, tv_mu=None, node_prec=None, weighted_z=False, scs_eps=None,
                        check_every=1, node_group=None, fuse_pupdate=True, device=None, return_engine=False,
                        distributed=None, ax_refresh_every=10, exchange="auto", gather="all", exchange_phases=None, partition="auto",
-                       acceptance=True, max_tighten=2, carry_residual=True,
+                       acceptance=True, max_tighten=2, carry_residual=False,
                        **kwargs):
     """Returns x_per_node as list of reconstructions, each length n, and the history of residual norms
     (block_6_admm_loop_ver2.py:21-24).
 
     `max_inner_iters` caps the CG iterations per TV sweep (it is unused in the reference, :17); `cg_iters`,
-    `tv_sweeps`, `tv_mu` select the work of ONE inner solve.  `acceptance` (default on, like the reference) applies
+    `tv_sweeps`, `tv_mu` select the work of ONE inner solve (default 1 sweep x 2 CG iterations: what decides the
+    accuracy of the x-update is the number of TV sweeps, not the CG count -- profiles/r2_inner_schedule_study.json,
+    DESIGN.md section 5).  `acceptance` (default on, like the reference) applies
     the accept / tighten-and-retry rule of :100-108,155-176 on the device: after a solve the stationarity norm
     |g_x,i| (:137-149) is compared with eps_target = 2/(k+1)^1.005; a node that misses it is solved again, warm
     started, at most `max_tighten` = 2 more times (masked launches, no host round trip); `eps_used_history` holds the

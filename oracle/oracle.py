@@ -507,7 +507,7 @@ def np_x_update(op, prec, rhs0, rhoD, mu, lam, S, C, x, d, w):
 
 def decentralized_admm(ops, sinograms, G, Wi_list, Qij_diag_fn, N, lam_tv=0.01, rho=1.0, max_iters=10,
                        eps_pri=1e-1, eps_dual=1e-1, phantom_true=None, node_prec=None, tv_mu=None,
-                       tv_sweeps=1, cg_iters=8, weighted_z=False, uniform_q=None, stop=True,
+                       tv_sweeps=1, cg_iters=2, weighted_z=False, uniform_q=None, stop=True,
                        x_update_fn=None, node_subset=None, acceptance=True, max_tighten=2, on_iteration=None):
     """Array restatement of block_6_admm_loop_ver2.py:15-326 with the SCS solve (:97-176) replaced by the
     TV-split + CG x-update.  Same initialisation (:36-46), Jacobi node sweep (:81-97,187), metrics (:189-206),

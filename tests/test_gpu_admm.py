@@ -222,7 +222,8 @@ def test_cfg4_size_iteration_is_deterministic_and_self_consistent():
     plan.close()
     sinos = [s[plan.ang_ptr[i]:plan.ang_ptr[i + 1]] for i in range(V)]
     G = make_graph("er", V, seed=0, p=0.1)
-    kw = dict(lam_tv=0.02, rho=2.0, max_iters=3, eps_pri=0.0, eps_dual=0.0, verbose=False, phantom_true=img, cg_iters=8)
+    kw = dict(lam_tv=0.02, rho=2.0, max_iters=3, eps_pri=0.0, eps_dual=0.0, verbose=False, phantom_true=img, cg_iters=8,
+              acceptance=False)
     x1, h1 = decentralized_admm(ops, sinos, G, None, None, N, **kw)
     x2, h2 = decentralized_admm(ops, sinos, G, None, None, N, **kw)
     assert h1["primal"] == h2["primal"] and h1["dual"] == h2["dual"]
@@ -260,7 +261,7 @@ def test_cfg1_full_size_200_iterations():
         _compare(hg, ho, xg, xo, img, N, iters, report=f"cfg1 128^2 x{iters} acceptance={acc} S={S} C={C}")
         if acc:
             t = np.array(hg["tighten_history"])
-            assert t.max() == 2 and t.min() == 0
+            assert t.max() == 2 and t.min() >= 0 and t[0].max() < 2
 
 
 def _cfg_problem_gpu_sinos(N, M, V, hetero):
