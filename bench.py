@@ -325,10 +325,10 @@ def main():
     ap.add_argument("--acceptance", type=int, default=1, choices=[0, 1],
                     help="1: the reference's accept / tighten-and-retry rule (block_6_ver2:100-176) on the device: up to "
                          "3 solves of tv_sweeps x cg_iters per node and iteration")
-    ap.add_argument("--carry", action="store_true",
-                    help="carry the CG residual across TV passes / outer iterations instead of rebuilding it with a "
-                         "back-projection at every solve (-0.75 ms at cfg4, but the fp32 recurrence drifts: 200-iteration "
-                         "trace error 2e-4 .. 6e-3 instead of 4e-6)")
+    ap.add_argument("--carry", default="iteration", choices=["iteration", "always", "off"],
+                    help="CG residual between solves: rebuilt by a back-projection at the first solve of every outer "
+                         "iteration and carried by the TV pass within it (default), carried across iterations too "
+                         "(drifts in fp32), or rebuilt at every solve")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="no per-kernel CUDA events in the timed region")
@@ -368,7 +368,7 @@ def main():
                      tv_sweeps=S, cg_iters=C, phantom_true=img, device=local, dist=dist if world > 1 else None,
                      rank=rank, world=world, node_group=args.node_group or None, fuse_pupdate=not args.no_fuse,
                      max_iters=total, exchange=args.exchange, exchange_phases=args.exchange_phases, partition=args.partition,
-                     acceptance=bool(args.acceptance), carry_residual=args.carry)
+                     acceptance=bool(args.acceptance), carry_residual=(False if args.carry == 'off' else args.carry))
 
     args.exchange_used = "push" if (eng.exchange_mode == "p2p" and getattr(eng, "_push", False)) else eng.exchange_mode
     args.phases_used = eng.phases
@@ -395,7 +395,7 @@ def main():
         nat.profile_read()
     eng.time_exchange = world > 1
     clocks = ClockSampler(local) if rank == 0 else None
-    l0 = nat.launch_count()
+    l0 = nat.launch_count() + eng.replayed_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.time()
     e0.record()
@@ -405,7 +405,8 @@ def main():
     barrier()
     tw1 = time.time()
     ms = e0.elapsed_time(e1)
-    launches = nat.launch_count() - l0
+    launches = nat.launch_count() + eng.replayed_launches - l0
+    graph_replay = bool(eng.use_graph and eng._graphs and not prof_inline)
     kprof = nat.profile_read() if prof_inline else {}
     nat.profile_enable(False)
     ms_prof = ms
@@ -523,7 +524,7 @@ def main():
                                           node_group=args.node_group or None, fuse_pupdate=not args.no_fuse,
                                           return_engine=True, exchange=args.exchange, gather="rank0",
                                           exchange_phases=args.exchange_phases, partition=args.partition,
-                                          acceptance=bool(args.acceptance), carry_residual=args.carry)
+                                          acceptance=bool(args.acceptance), carry_residual=(False if args.carry == 'off' else args.carry))
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -548,7 +549,10 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg, G),
-                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+                "launch_mode": ("CUDA-graph replay of the outer iteration (launch count = kernel nodes replayed)" if graph_replay
+                                else "eager launches (per-kernel CUDA events ride in the timed region)"),
+                "roofline": roof,
                 "iteration_roofline": it_roof, "exchange": exch, "cpu_baseline": cpu, "kernels": kernels,
                 "residuals_after": {"primal": pri, "dual": dual, "iterations": eng_iters}}
         print(json.dumps(line), flush=True)

@@ -53,7 +53,8 @@ class State(ctypes.Structure):
         ("stride", ctypes.c_longlong), ("rho", ctypes.c_float), ("lam", ctypes.c_float), ("mu", ctypes.c_float),
         ("q_uniform", ctypes.c_float), ("w_parity", ctypes.c_int), ("fuse_pupdate", ctypes.c_int),
         ("defer_tv", ctypes.c_int), ("reuse_ax", ctypes.c_int), ("ctl", ctypes.c_void_p), ("masked", ctypes.c_int),
-        ("carry_r", ctypes.c_int), ("reuse_r", ctypes.c_int)]
+        ("carry_r", ctypes.c_int), ("reuse_r", ctypes.c_int), ("iter_dev", ctypes.c_void_p),
+        ("hist_stride", ctypes.c_longlong)]
 
 
 EDGE_FIELDS = ("xi", "xj", "yi", "yj", "z", "ai", "aj", "Wi", "Wj", "qij", "qji")  # struct admm_edge (u64 each)
@@ -129,8 +130,18 @@ KC_NAMES = ("fwd", "fwd_reduce", "back_plain", "back_hp", "back_resid0", "colnor
             "sino_axpy", "sino_resid", "rhs0", "edge", "pack", "finalize", "fwd_fused", "accept")
 
 
+_profiling = False
+
+
 def profile_enable(on: bool) -> None:
+    global _profiling
     check(lib().admm_profile_enable(1 if on else 0), "admm_profile_enable")
+    _profiling = bool(on)
+
+
+def profiling() -> bool:
+    """True while the per-launch CUDA-event profiler is on (event records cannot be captured into a CUDA graph)."""
+    return _profiling
 
 
 def profile_read() -> dict:

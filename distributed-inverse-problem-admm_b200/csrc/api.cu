@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -18,9 +19,10 @@ static_assert(sizeof(admm_pack_item) == sizeof(PackDesc), "pack descriptor layou
 static_assert(sizeof(admm_node_ctl) == sizeof(NodeCtl), "node control layout");
 
 namespace admm {
-long long g_launch_count = 0;
-bool g_prof_on = false;
+std::atomic<long long> g_launch_count{0};
+std::atomic<bool> g_prof_on{false};
 struct ProfRec { int kc; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;              // the record list and the event pool may be touched from several host threads
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_pool;
 static cudaEvent_t prof_event() {
@@ -28,6 +30,7 @@ static cudaEvent_t prof_event() {
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 void prof_mark(int kc, cudaStream_t st, bool begin) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     if (begin) {
         ProfRec r{kc, prof_event(), prof_event()};
         cudaEventRecord(r.e0, st);
@@ -47,6 +50,7 @@ extern "C" int admm_profile_enable(int on) {
 extern "C" int admm_profile_read(double* ms, long long* cnt) {
     if (!ms || !cnt) return ADMM_ERR_ARG;
     if (cudaDeviceSynchronize() != cudaSuccess) return ADMM_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(admm::g_prof_mu);
     for (auto& r : admm::g_prof) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms[r.kc] += t; cnt[r.kc] += 1; }
@@ -101,7 +105,7 @@ extern "C" long long admm_abi_sizeof(int what) {
     return -1;
 }
 extern "C" const char* admm_last_error(void) { return g_err.c_str(); }
-extern "C" long long admm_launch_count(void) { return admm::g_launch_count; }
+extern "C" long long admm_launch_count(void) { return admm::g_launch_count.load(); }
 extern "C" int admm_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -513,6 +517,7 @@ extern "C" int admm_accept(admm_plan* p, admm_state* s, int node0, int nodes, do
     AcceptParams A{};
     A.ctl = reinterpret_cast<NodeCtl*>(s->ctl); A.scal = s->scal; A.node0 = node0; A.nodes = nodes;
     A.first = first; A.max_tighten = max_tighten; A.eps_target2 = eps_target * eps_target;
+    A.iter_dev = s->iter_dev;
     CK(launch_accept(A, (cudaStream_t)stream));
     return ADMM_OK;
 }
@@ -551,6 +556,7 @@ extern "C" int admm_finalize(admm_plan* p, const admm_state* s, const double* d_
     F.node_gid = d_node_gid; F.row = d_row; F.E = nedges; F.E_local = nedges_local; F.V = p->V; F.Vg = Vg; F.rho = s->rho;
     F.nbr_ptr = d_nbr_ptr; F.nbr_epos = d_nbr_epos; F.nbr_end = d_nbr_end;
     F.ctl = reinterpret_cast<const NodeCtl*>(s->ctl);
+    F.iter_dev = s->iter_dev; F.hist_stride = s->hist_stride;
     CK(launch_finalize(F, (cudaStream_t)stream));
     return ADMM_OK;
 }

@@ -3,9 +3,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace admm {
 
-extern long long g_launch_count;  // kernels launched by this library (bench evidence)
+extern std::atomic<long long> g_launch_count;  // kernels launched by this library (bench evidence)
 
 // kernel classes for the optional CUDA-event profiler (admm_profile_* in the C ABI)
 enum KClass : int {
@@ -13,7 +15,7 @@ enum KClass : int {
     KC_P_UPDATE, KC_SINO_AXPY, KC_SINO_RESID, KC_RHS0, KC_EDGE, KC_PACK, KC_FINALIZE, KC_FWD_FUSED, KC_ACCEPT, KC_COUNT
 };
 void prof_mark(int kc, cudaStream_t st, bool begin);
-extern bool g_prof_on;
+extern std::atomic<bool> g_prof_on;
 struct ProfScope {  // records a CUDA event pair around one launch on its own stream when profiling is on
     int kc; cudaStream_t st;
     ProfScope(int k, cudaStream_t s) : kc(k), st(s) { ++g_launch_count; if (g_prof_on) prof_mark(kc, st, true); }

@@ -4,6 +4,8 @@
 // Replaces odl.tomo.RayTransform.__call__ / `Ai @ x` (block_2_load_odl_data.py:149,
 // block_6_admm_loop_ver2.py:145,193), `Ai.T @ r` (block_6_admm_loop_ver2.py:145) and
 // np.sum(A_i*A_i, axis=0) (block_3_graph_and_precisions.py:22).  Discretisation: SURVEY.md App. C.
+#include <mutex>
+
 #include "projector.cuh"
 
 namespace admm {
@@ -591,13 +593,23 @@ static size_t fwd_smem_bytes(int span) {
 
 cudaError_t launch_forward(const FwdParams& P, int nodes, int max_chunks, const FwdReduceParams& R,
                            cudaStream_t st) {
-    static int configured_span = -1;
+    // the dynamic shared-memory limit is a per-device function attribute: remember what was set on EACH device
+    static std::mutex mu;
+    static int configured_span[64];
+    static bool init = false;
     const size_t smem = fwd_smem_bytes(P.span);
-    if (configured_span < P.span) {
-        cudaError_t e = cudaFuncSetAttribute(fwd_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)fwd_smem_bytes(P.span));
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!init) { for (int& v : configured_span) v = -1; init = true; }
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        configured_span = P.span;
+        const int slot = (dev >= 0 && dev < 64) ? dev : 63;
+        if (dev >= 63 || configured_span[slot] < P.span) {
+            e = cudaFuncSetAttribute(fwd_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured_span[slot] = P.span;
+        }
     }
     dim3 grid(P.nTi * P.nSeg * max_chunks, nodes, 2);
     { ProfScope ps(P.mode ? KC_FWD_FUSED : KC_FWD, st); fwd_strip_kernel<<<grid, FTHREADS, smem, st>>>(P); }

@@ -44,6 +44,7 @@ struct AcceptParams {      // a14 acceptance decision (block_6_admm_loop_ver2.py
     NodeCtl* ctl; const double* scal;
     int node0, nodes, first, max_tighten;
     double eps_target2;    // eps_target^2, eps_target = 2 / (k+1)^1.005 (:101-103)
+    const int* iter_dev;   // device-resident outer iteration counter k (CUDA-graph replay): overrides eps_target2
 };
 
 struct RhsParams {
@@ -91,7 +92,9 @@ struct FinalizeParams {
     const int* nbr_epos;      // [nnz] position of the edge in the sums / flags arrays
     const int* nbr_end;       // [nnz] 0: the node is the edge's min end, 1: max end
     const NodeCtl* ctl;       // [V] or nullptr: tries of the a14 rule -> row block 7
-    double* row;              // [2 + 8*Vg]
+    double* row;              // [2 + 8*Vg]  (iter_dev set: base of the history, row k = row + k * hist_stride)
+    int* iter_dev;            // device-resident outer iteration counter, incremented here (or nullptr)
+    long long hist_stride;
     int E, E_local, V, Vg;    // edges [E_local, E) are the cut edges
     float rho;
 };

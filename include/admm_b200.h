@@ -82,6 +82,11 @@ typedef struct admm_state {
                                  then starts without the A^T(P A x) back-projection of its residual                  */
     int reuse_r;              /* 1: r, p0 and <r,r> are current for the solve that follows (set 0 periodically, and for
                                  the first solve, to rebuild r = rhs0 + tvterm - H x and stop fp32 drift)             */
+    int* iter_dev;            /* device-resident outer iteration counter k, or NULL.  When set (CUDA-graph replay of the
+                                 outer iteration: nothing host-side may change between replays), admm_accept derives
+                                 eps_target = 2/(k+1)^1.005 from it on the device, and admm_finalize treats d_row as the
+                                 base of the history, writes row k at d_row + k*hist_stride and increments k          */
+    long long hist_stride;    /* doubles between history rows (with iter_dev)                                          */
 } admm_state;
 
 /* Per-node control word (block_6_admm_loop_ver2.py:110-113 `accepted`, `tighten_tries`): zero-initialised by the
