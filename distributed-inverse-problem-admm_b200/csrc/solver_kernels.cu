@@ -16,6 +16,7 @@ namespace admm {
 // (float4 loads / stores) and recomputes the (d - w') of its upper and left neighbours in registers, so there is
 // no shared-memory tile, no barrier before the reduction and every global access is a coalesced 16-byte one.
 constexpr int TVX = 32, TVY = 8;
+constexpr int TV_MIN_BLOCKS = 3;   // 79 registers, no spills (4 would cap at 64 registers and spill)
 
 struct Dw { float dwx, dwy, w1, w2; };
 
@@ -53,7 +54,7 @@ __device__ __forceinline__ void load_seg(const float* __restrict__ row, int c, i
     (void)vec;
 }
 
-__global__ void __launch_bounds__(TVX * TVY, 3)
+__global__ void __launch_bounds__(TVX * TVY, TV_MIN_BLOCKS)
 tv_fused_kernel(const TvParams P) {
     __shared__ __align__(16) float red[128];
     // (d - w')_x and the unit-gradient x-component of every pixel of the block, for the row below; the y-components
