@@ -7,4 +7,5 @@ declared in include/admm_b200.h.  There is no CPU fallback.
 from . import _native, registry  # noqa: F401
 from .geometry import (angle_split, default_angles_total, graph_csr, make_graph, node_angles, node_to_gpu,  # noqa: F401
                        psnr, shepp_logan, trig_table32)
-from .operators import DiscreteSpace, Element, Plan, RayTransformCUDA, stack_operators  # noqa: F401
+from .operators import (DenseOperatorCUDA, DensePlan, DiscreteSpace, Element, Plan, RayTransformCUDA,  # noqa: F401
+                        make_plan, stack_operators)

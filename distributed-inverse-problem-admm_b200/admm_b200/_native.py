@@ -14,7 +14,7 @@ _ROOT = os.path.dirname(_PKG)                      # distributed-inverse-problem
 CSRC = os.path.join(_ROOT, "csrc")
 LIB_PATH = os.path.join(_ROOT, "libadmm_b200.so")
 HEADER = os.path.join(os.path.dirname(_ROOT), "include", "admm_b200.h")
-SOURCES = ["api.cu", "projector.cu", "solver_kernels.cu", "tv_helpers.cu"]
+SOURCES = ["api.cu", "projector.cu", "solver_kernels.cu", "tv_helpers.cu", "dense.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -79,6 +79,10 @@ def lib():
     L.admm_launch_count.restype = ll
     L.admm_plan_create.restype = vp
     L.admm_plan_create.argtypes = [i, i, d, i, vp, vp, vp, i]
+    L.admm_plan_create_dense.restype = vp
+    L.admm_plan_create_dense.argtypes = [i, i, vp, i]
+    L.admm_plan_upload_dense.restype = i
+    L.admm_plan_upload_dense.argtypes = [vp, i, vp]
     L.admm_plan_destroy.argtypes = [vp]
     L.admm_plan_destroy.restype = None
     L.admm_plan_info.restype = ll
@@ -118,7 +122,8 @@ def lib():
     return L
 
 
-EXPORTS = ("admm_version", "admm_abi_sizeof", "admm_last_error", "admm_device_count", "admm_plan_create", "admm_plan_destroy",
+EXPORTS = ("admm_version", "admm_abi_sizeof", "admm_last_error", "admm_device_count", "admm_plan_create",
+           "admm_plan_create_dense", "admm_plan_upload_dense", "admm_plan_destroy",
            "admm_plan_info", "admm_plan_set", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host",
            "admm_adjoint_host", "admm_colnorm2_host", "admm_rhs0", "admm_x_update", "admm_edge_update", "admm_pack", "admm_finalize",
            "admm_tv_pass", "admm_accept", "admm_launch_count", "admm_profile_enable", "admm_profile_read", "admm_grad2d_host",

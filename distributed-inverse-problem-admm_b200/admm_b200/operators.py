@@ -84,6 +84,103 @@ class Plan:
                   "admm_colnorm2")
 
 
+class DensePlan(Plan):
+    """Plan over explicit dense matrices (the reference's literal `A_dense_list` ndarrays, uploaded once): same
+    interface as `Plan` with D = 1 and A = total matrix rows.  Tiny problems only -- 4 m_i n bytes per node."""
+
+    def __init__(self, N, mats, device=0):
+        nat.require_cuda()
+        self.N, self.D, self.det_w, self.device = int(N), 1, 2.0, int(device)
+        self.n = self.N * self.N
+        mats = [np.ascontiguousarray(np.asarray(A, dtype=np.float32)) for A in mats]
+        for A in mats:
+            if A.ndim != 2 or A.shape[1] != self.n:
+                raise ValueError(f"dense operator of shape {A.shape} does not map {self.N}x{self.N} images")
+        self.V = len(mats)
+        self.thetas = None
+        self.ang_ptr = np.zeros(self.V + 1, dtype=np.int32)
+        self.ang_ptr[1:] = np.cumsum([A.shape[0] for A in mats])
+        self.A = int(self.ang_ptr[-1])
+        L = nat.lib()
+        h = L.admm_plan_create_dense(self.N, self.V, self.ang_ptr.ctypes.data, self.device)
+        if not h:
+            raise RuntimeError("admm_plan_create_dense failed: " + L.admm_last_error().decode())
+        self.handle = ctypes.c_void_p(h)
+        for i, A in enumerate(mats):
+            nat.check(L.admm_plan_upload_dense(self.handle, i, A.ctypes.data), "admm_plan_upload_dense")
+        self.part_floats = int(L.admm_plan_info(self.handle, nat.INFO_PART_FLOATS))
+
+
+def make_plan(N, ops, D=None, det_w=2.0, device=0):
+    """One plan over the operators of the nodes resident on a GPU: matrix-free (`RayTransformCUDA`: angle arrays) or
+    dense (`DenseOperatorCUDA` / 2-D ndarrays)."""
+    dense = [isinstance(o, DenseOperatorCUDA) or (isinstance(o, np.ndarray) and o.ndim == 2) for o in ops]
+    if all(dense):
+        return DensePlan(N, [o.matrix if isinstance(o, DenseOperatorCUDA) else o for o in ops], device)
+    if any(dense):
+        raise TypeError("mixing dense matrices and matrix-free operators in one A_dense_list is not supported")
+    return Plan(N, [np.asarray(o.angles if hasattr(o, "angles") else o, dtype=np.float64) for o in ops], D, det_w, device)
+
+
+class DenseOperatorCUDA:
+    """A dense (m, n) matrix behind the operator interface the drop-ins use (`.shape`, `@`, `.T @`, `.colnorm2()`),
+    evaluated by the dense kernels of libadmm_b200.so.  Stands for an `A_dense_list[i]` ndarray
+    (block_2_load_odl_data.py:68-96)."""
+
+    is_dense = True
+
+    def __init__(self, A, N=None, device=0):
+        self.matrix = np.ascontiguousarray(np.asarray(A, dtype=np.float32))
+        if self.matrix.ndim != 2:
+            raise ValueError("a dense operator is a 2-D matrix")
+        self.shape = self.matrix.shape
+        self.N = int(N) if N is not None else int(round(math.sqrt(self.shape[1])))
+        if self.N * self.N != self.shape[1]:
+            raise ValueError(f"{self.shape[1]} columns is not a square image")
+        self.D, self.det_w, self.device = 1, 2.0, int(device)
+        self._plan = None
+
+    def plan(self):
+        if self._plan is None:
+            self._plan = DensePlan(self.N, [self.matrix], self.device)
+        return self._plan
+
+    def _forward_np(self, x):
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float32).reshape(-1))
+        out = np.empty(self.shape[0], dtype=np.float32)
+        nat.check(nat.lib().admm_forward_host(self.plan().handle, 0, x.ctypes.data, out.ctypes.data), "admm_forward_host")
+        return out
+
+    def _adjoint_np(self, y):
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float32).reshape(-1))
+        out = np.empty(self.shape[1], dtype=np.float32)
+        nat.check(nat.lib().admm_adjoint_host(self.plan().handle, 0, y.ctypes.data, out.ctypes.data), "admm_adjoint_host")
+        return out
+
+    def __matmul__(self, x):
+        x = np.asarray(x)
+        out = self._forward_np(x)
+        return out.astype(np.float64) if x.dtype == np.float64 else out
+
+    @property
+    def T(self):
+        op = self
+
+        class _T:
+            shape = (op.shape[1], op.shape[0])
+
+            def __matmul__(self, y):
+                y = np.asarray(y)
+                out = op._adjoint_np(y)
+                return out.astype(np.float64) if y.dtype == np.float64 else out
+        return _T()
+
+    def colnorm2(self):
+        out = np.empty(self.shape[1], dtype=np.float32)
+        nat.check(nat.lib().admm_colnorm2_host(self.plan().handle, 0, out.ctypes.data), "admm_colnorm2_host")
+        return out.astype(np.float64)
+
+
 # ---- ODL-shaped spaces / elements (block_2_load_odl_data.py:87-93,145-154; ADMM_Tomo_Only.py usage) -------
 class Element:
     def __init__(self, space, arr):

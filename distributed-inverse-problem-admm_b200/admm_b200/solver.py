@@ -12,13 +12,18 @@ import math
 import numpy as np
 
 from . import _native as nat
-from .operators import Plan
+from .operators import DenseOperatorCUDA, make_plan
 from .sharding import ShardPlan, build_shard_plan, partition_nodes, phase_bounds, post_exchange
 
 
 def _torch():
     import torch
     return torch
+
+
+def _rows(t):
+    """Work weight of a node's operator: its number of projection angles, or matrix rows for a dense operator."""
+    return int(t.shape[0]) if hasattr(t, "shape") and len(getattr(t, "shape", ())) == 2 else len(t)
 
 
 HIST_KEYS = ("primal", "dual", "pri_per_node", "dual_per_node", "obj_per_node", "obj_total", "mse_sino_per_node",
@@ -29,7 +34,8 @@ HIST_KEYS = ("primal", "dual", "pri_per_node", "dual_per_node", "obj_per_node", 
 class ADMMEngine:
     """One rank's share of the solve.
 
-    thetas      per global node angle arrays (radians)
+    thetas      per global node angle arrays (radians) -- or dense operators (DenseOperatorCUDA / 2-D ndarrays: the
+                reference's literal A_dense_list, tiny problems only)
     sinograms   per global node (M_i, D) arrays (only the local ones are uploaded)
     G           networkx graph on 0..V-1
     Q           None / float -> uniform Q_ij = q (D_i = deg_i q);  callable (i, j) -> n-vector otherwise
@@ -76,7 +82,7 @@ class ADMMEngine:
             # every rank sees the same graph, so every rank raises here -- before any collective can hang
             raise ValueError(f"{self.world} ranks but only {G.number_of_nodes()} graph nodes: a rank would own no node")
         # (balanced by node count AND by angle rows: the projector kernels' time follows the angles a rank holds)
-        self.node_rank = (partition_nodes(G, self.world, partition, weights=[len(t) for t in thetas])
+        self.node_rank = (partition_nodes(G, self.world, partition, weights=[_rows(t) for t in thetas])
                           if isinstance(partition, str) else [int(r) for r in partition])
         self.sp: ShardPlan = build_shard_plan(G, self.world, self.rank, self.phases, self.node_rank)
         sp = self.sp
@@ -87,7 +93,10 @@ class ADMMEngine:
             raise ValueError("rank owns no node (more ranks than nodes)")
         n = self.n
         f32 = dict(dtype=torch.float32, device=self.dev)
-        self.plan = Plan(N, [thetas[g] for g in self.loc], self.D, det_w, device)
+        self.plan = make_plan(N, [thetas[g] for g in self.loc], self.D, det_w, device)
+        self.dense = bool(getattr(self.plan, "thetas", None) is None)
+        if self.dense:      # explicit matrices: "sinograms" are plain vectors, and the fused CG staging does not apply
+            self.D, fuse_pupdate = 1, 0
         A = self.A = self.plan.A
         self.node_group = int(node_group) if node_group else V
         self.ax_refresh_every = max(1, int(ax_refresh_every))
@@ -178,7 +187,7 @@ class ADMMEngine:
         self.iter_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
         # the outer iteration as a CUDA graph (single GPU): ~15 C-ABI calls / 20-60 launches per iteration replay as
         # one submission -- what makes the small, launch-bound configs (cfg 1, 2, 5) run at kernel speed
-        self.use_graph = (self.world == 1) if cuda_graph == "auto" else bool(cuda_graph)
+        self.use_graph = ((self.world == 1) if cuda_graph == "auto" else bool(cuda_graph)) and not self.dense
         self._graphs = {}
         self.replayed_launches = 0     # kernels launched through graph replays (the library's own counter sees only eager launches)
         self.W = None
@@ -725,15 +734,17 @@ class NodeProblem:
     def __init__(self, op, b, rho, neighbor_terms, N, lam_tv, Qij_terms, tv_mu=None, device=None, prec=1.0):
         torch = _torch()
         nat.require_cuda()
-        if not hasattr(op, "angles"):
-            raise TypeError("Ai must be a matrix-free RayTransformCUDA operator (no dense / CPU path)")
+        if isinstance(op, np.ndarray) and op.ndim == 2:
+            op = DenseOperatorCUDA(op, N)          # the reference's literal dense Ai (block_5_node_problem.py:8)
+        if not (hasattr(op, "angles") or isinstance(op, DenseOperatorCUDA)):
+            raise TypeError("Ai must be a RayTransformCUDA operator or a dense (m, n) matrix")
         device = op.device if device is None else device
         self.torch, self.dev = torch, torch.device(f"cuda:{device}")
         torch.cuda.set_device(self.dev)
         self.N, self.n, self.D = int(N), int(N) * int(N), op.D
         self.rho, self.lam = float(rho), float(lam_tv)
         self.mu = float(tv_mu) if tv_mu is not None else (self.rho if self.rho > 0 else 1.0)
-        self.plan = Plan(N, [op.angles], op.D, op.det_w, device)
+        self.plan = make_plan(N, [op], op.D, op.det_w, device)
         n, f32 = self.n, dict(dtype=torch.float32, device=self.dev)
         up = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))).to(self.dev)  # noqa: E731
         self.b = up(b).reshape(self.plan.A, self.D)
@@ -764,7 +775,7 @@ class NodeProblem:
             setattr(st, name, getattr(self, name).data_ptr())
         st.xtrue = None
         st.stride, st.rho, st.lam, st.mu, st.q_uniform = n, self.rho, self.lam, self.mu, 1.0
-        st.w_parity, st.fuse_pupdate = 0, 2
+        st.w_parity, st.fuse_pupdate = 0, (0 if isinstance(op, DenseOperatorCUDA) else 2)
         ptr = torch.tensor([0, deg], dtype=torch.int32, device=self.dev)
         a = lambda t, k: t.data_ptr() + k * n * 4  # noqa: E731
         i64 = lambda v: torch.tensor(v if v else [0], dtype=torch.int64, device=self.dev)  # noqa: E731

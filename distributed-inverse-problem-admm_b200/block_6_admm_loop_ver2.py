@@ -21,22 +21,35 @@ _IGNORED = ("scs_total_iters", "scs_chunk_iters", "scs_snapshot_dir", "scs_use_i
             "scs_acceleration", "scs_lookback", "scs_scale", "scs_save_every_chunks", "edge_mask_provider")
 
 
-def _node_geometry(A_list):
-    """Per-node angle arrays and the common (N, D, det_w) from operator-shaped `A_dense_list` entries."""
-    thetas = []
-    geo = None
+def _node_geometry(A_list, N):
+    """Per-node operators for the engine -- angle arrays of matrix-free `RayTransformCUDA` entries, or dense operators
+    for literal ndarray entries (the reference's own `A_dense_list`, block_2_load_odl_data.py:68-96: uploaded, no
+    projector kernel, tiny problems only) -- and the common (N, D, det_w)."""
+    from admm_b200 import DenseOperatorCUDA
+    ops, geo, dense = [], None, 0
     for A in A_list:
-        if not hasattr(A, "angles"):
-            raise TypeError(
-                "A_dense_list entries must be matrix-free RayTransformCUDA operators (block_2_load_odl_data."
-                "load_odl_data builds them); dense matrices carry no geometry and there is no CPU/dense path")
-        g = (A.N, A.D, A.det_w)
+        if isinstance(A, np.ndarray) and A.ndim == 2:
+            A = DenseOperatorCUDA(A, N)
+        if isinstance(A, DenseOperatorCUDA):
+            dense += 1
+            g = (A.N, 1, 2.0)
+            ops.append(A)
+        elif hasattr(A, "angles"):
+            g = (A.N, A.D, A.det_w)
+            ops.append(np.asarray(A.angles, dtype=np.float64))
+        else:
+            raise TypeError("A_dense_list entries must be RayTransformCUDA operators (block_2_load_odl_data."
+                            "load_odl_data builds them) or dense (m_i, N*N) matrices")
         if geo is None:
             geo = g
         elif g != geo:
             raise ValueError("all node operators must share N, D and the detector width")
-        thetas.append(np.asarray(A.angles, dtype=np.float64))
-    return thetas, geo
+    if dense:
+        import warnings
+        mb = sum(int(np.prod(o.shape)) for o in ops if hasattr(o, "matrix")) * 4 / 2 ** 20
+        warnings.warn(f"decentralized_admm: {dense} dense operator(s) ({mb:.0f} MiB) are uploaded as they are and applied with "
+                      f"plain dense matvec kernels; the matrix-free RayTransformCUDA operators are the fast path")
+    return ops, geo
 
 
 def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
@@ -80,7 +93,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
         raise ValueError("G is None: build_pixel_connected_Q_provider returns a graph only with plot_union=True "
                          "in the reference (SURVEY App. B-8); this build always returns one")
     num_nodes = len(A_dense_list)
-    thetas, (Ng, D, det_w) = _node_geometry(A_dense_list)
+    thetas, (Ng, D, det_w) = _node_geometry(A_dense_list, N)
     if Ng != N:
         raise ValueError(f"N={N} does not match the operators' image size {Ng}")
     n = N * N

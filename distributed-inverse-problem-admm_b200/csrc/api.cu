@@ -92,7 +92,22 @@ struct admm_plan {
     float* d_hsino = nullptr;
     int hsino_rows = 0;
     int pack_blocks = 0;             // ADMM_OPT_PACK_BLOCKS (0: one block row per item)
+    // dense-matrix plans (admm_plan_create_dense): A = total matrix rows, D = 1, d_dense = [A][N*N] row-major
+    bool dense = false;
+    float* d_dense = nullptr;
 };
+
+static int check_nodes(const admm_plan* p, int node0, int nodes);
+
+// the operator pair of a plan: strip projector / tile back-projector, or the dense matvecs
+static cudaError_t plan_forward(const admm_plan* p, const FwdParams& F, int nodes, const FwdReduceParams& R, cudaStream_t st) {
+    if (p->dense) return launch_dense_forward(p->d_dense, p->d_anode, F, nodes, R, st);
+    return launch_forward(F, nodes, p->max_chunks, R, st);
+}
+static cudaError_t plan_back(const admm_plan* p, int mode, const BackParams& B, int nodes, cudaStream_t st) {
+    if (p->dense) return launch_dense_back(p->d_dense, mode, B, nodes, st);
+    return launch_back(mode, B, nodes, st);
+}
 
 extern "C" int admm_version(void) { return 200; }
 extern "C" long long admm_abi_sizeof(int what) {
@@ -227,10 +242,58 @@ extern "C" admm_plan* admm_plan_create(int N, int D, double det_w, int V, const 
     return p;
 }
 
+// Dense-matrix plan: node i's operator is an explicit (row_ptr[i+1]-row_ptr[i]) x N*N float32 matrix, uploaded with
+// admm_plan_upload_dense.  "Sinogram" arrays of such a plan are [rows][1].
+extern "C" admm_plan* admm_plan_create_dense(int N, int V, const int* row_ptr, int device) {
+    if (N < 2 || V < 1 || !row_ptr) {
+        fail(ADMM_ERR_ARG, "admm_plan_create_dense: bad argument");
+        return nullptr;
+    }
+    if (admm_device_count() <= device) {
+        fail(ADMM_ERR_CUDA, "admm_plan_create_dense: no CUDA device (this library has no CPU fallback)");
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        fail(ADMM_ERR_CUDA, "cudaSetDevice failed");
+        return nullptr;
+    }
+    admm_plan* p = new admm_plan();
+    p->N = N; p->D = 1; p->V = V; p->device = device; p->dense = true;
+    p->aptr.assign(row_ptr, row_ptr + V + 1);
+    p->A = row_ptr[V];
+    const int A = std::max(p->A, 1);
+    std::vector<int> anode(A, 0);
+    for (int v = 0; v < V; ++v)
+        for (int a = row_ptr[v]; a < row_ptr[v + 1]; ++a) anode[a] = v;
+    const size_t bytes = (size_t)A * N * N * sizeof(float);
+    bool ok = cudaMalloc(&p->d_aptr, sizeof(int) * (V + 1)) == cudaSuccess;
+    ok = ok && cudaMalloc(&p->d_anode, sizeof(int) * A) == cudaSuccess;
+    ok = ok && cudaMalloc(&p->d_dense, bytes) == cudaSuccess;
+    ok = ok && cudaMemcpy(p->d_aptr, row_ptr, sizeof(int) * (V + 1), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(p->d_anode, anode.data(), sizeof(int) * A, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        fail(ADMM_ERR_CUDA, std::string("admm_plan_create_dense: ") + cudaGetErrorString(cudaGetLastError()));
+        admm_plan_destroy(p);
+        return nullptr;
+    }
+    p->ws_bytes = (long long)bytes;
+    return p;
+}
+
+extern "C" int admm_plan_upload_dense(admm_plan* p, int node, const float* h_A) {
+    if (int e = check_nodes(p, node, 1)) return e;
+    if (!p->dense || !h_A) return fail(ADMM_ERR_ARG, "admm_plan_upload_dense: not a dense plan / null matrix");
+    CK(cudaSetDevice(p->device));
+    const size_t n = (size_t)p->N * p->N;
+    const int r0 = p->aptr[node], r1 = p->aptr[node + 1];
+    CK(cudaMemcpy(p->d_dense + (size_t)r0 * n, h_A, (size_t)(r1 - r0) * n * sizeof(float), cudaMemcpyHostToDevice));
+    return ADMM_OK;
+}
+
 extern "C" void admm_plan_destroy(admm_plan* p) {
     if (!p) return;
     cudaFree(p->d_ang); cudaFree(p->d_optr); cudaFree(p->d_oidx); cudaFree(p->d_aptr); cudaFree(p->d_anode);
-    cudaFree(p->d_recs); cudaFree(p->d_jstart); cudaFree(p->d_himg); cudaFree(p->d_hsino);
+    cudaFree(p->d_recs); cudaFree(p->d_jstart); cudaFree(p->d_himg); cudaFree(p->d_hsino); cudaFree(p->d_dense);
     delete p;
 }
 
@@ -255,7 +318,8 @@ extern "C" long long admm_plan_info(const admm_plan* p, int what) {
         case ADMM_INFO_PART_FLOATS: {
             const long long tiles = (long long)((p->N + 31) / 32) * ((p->N + 31) / 32);       // back-projector grid
             const long long tvblk = (long long)((p->N + 127) / 128) * ((p->N + 7) / 8);       // TV grid
-            return std::max(std::max(3 * tiles, 4 * tvblk), 5LL * 4096);
+            const long long dblk = p->dense ? 3 * (((long long)p->N * p->N + 255) / 256) : 0;   // dense back-projector grid
+            return std::max(std::max(std::max(3 * tiles, 4 * tvblk), 5LL * 4096), dblk);
         }
         case ADMM_INFO_FWD_SPAN: return p->span;
         case ADMM_INFO_FWD_NREC: return (long long)p->nTi * p->nSeg;
@@ -293,7 +357,7 @@ extern "C" int admm_forward(admm_plan* p, const float* d_img, long long stride, 
     if (int e = check_nodes(p, node0, nodes)) return e;
     if (!d_img || !d_sino) return fail(ADMM_ERR_ARG, "admm_forward: null buffer");
     FwdParams P = make_fwd(p, d_img, stride, node0);
-    CK(launch_forward(P, nodes, p->max_chunks, make_red(p, d_sino, node0, nodes), (cudaStream_t)stream));
+    CK(plan_forward(p, P, nodes, make_red(p, d_sino, node0, nodes), (cudaStream_t)stream));
     return ADMM_OK;
 }
 
@@ -309,14 +373,14 @@ extern "C" int admm_adjoint(admm_plan* p, const float* d_sino, const float* d_pr
                             int node0, int nodes, void* stream) {
     if (int e = check_nodes(p, node0, nodes)) return e;
     if (!d_img || !d_sino) return fail(ADMM_ERR_ARG, "admm_adjoint: null buffer");
-    CK(launch_back(BACK_PLAIN, make_back(p, d_sino, d_prec, d_img, stride, node0), nodes, (cudaStream_t)stream));
+    CK(plan_back(p, BACK_PLAIN, make_back(p, d_sino, d_prec, d_img, stride, node0), nodes, (cudaStream_t)stream));
     return ADMM_OK;
 }
 
 extern "C" int admm_colnorm2(admm_plan* p, float* d_img, long long stride, int node0, int nodes, void* stream) {
     if (int e = check_nodes(p, node0, nodes)) return e;
     if (!d_img) return fail(ADMM_ERR_ARG, "admm_colnorm2: null buffer");
-    CK(launch_back(BACK_COLNORM2, make_back(p, nullptr, nullptr, d_img, stride, node0), nodes, (cudaStream_t)stream));
+    CK(plan_back(p, BACK_COLNORM2, make_back(p, nullptr, nullptr, d_img, stride, node0), nodes, (cudaStream_t)stream));
     return ADMM_OK;
 }
 
@@ -416,6 +480,8 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
                              void* stream) {
     if (int e = check_nodes(p, node0, nodes)) return e;
     if (!s || sweeps < 1 || cg_iters < 0) return fail(ADMM_ERR_ARG, "admm_x_update: bad argument");
+    if (p->dense && s->fuse_pupdate != 0)
+        return fail(ADMM_ERR_ARG, "admm_x_update: dense-matrix plans need fuse_pupdate = 0 (the fused CG staging lives in the strip projector)");
     cudaStream_t st = (cudaStream_t)stream;
     const long long n = (long long)p->N * p->N, off = (long long)node0 * s->stride;
     const long long part_per = admm_plan_info(p, ADMM_INFO_PART_FLOATS);
@@ -436,7 +502,7 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
         if (!(s->reuse_ax || sw > 0)) {   // later sweeps: ax is current by the recurrence
             FwdParams F = make_fwd(p, s->x + off, s->stride, node0);
             F.ctl = mask;
-            CK(launch_forward(F, nodes, p->max_chunks, make_red(p, s->ax, node0, nodes), st));
+            CK(plan_forward(p, F, nodes, make_red(p, s->ax, node0, nodes), st));
         }
         BackParams B = make_back(p, s->ax, s->prec, s->r + off, s->stride, node0);
         B.v = s->x + off; B.rhoD_vec = s->rhoD_vec ? s->rhoD_vec + off : nullptr; B.rhoD_s = s->rhoD_s; B.mu = s->mu;
@@ -444,7 +510,7 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
         B.part = part; B.counter = counter; B.scal = s->scal; B.dot_slot = S_RR0; B.ctl = mask;
         // with carry_r the TV pass (r += tvterm' - tvterm) and the rhs0 assembly (r += rhs0' - rhs0) keep r = rhs0 +
         // tvterm - H x, p0 = r and <r,r> current, so the solve starts without this back-projection
-        if (!(s->carry_r && (sw > 0 || s->reuse_r))) CK(launch_back(BACK_RESID0, B, nodes, st));
+        if (!(s->carry_r && (sw > 0 || s->reuse_r))) CK(plan_back(p, BACK_RESID0, B, nodes, st));
         int cur = 0;
         float* rcur = s->r + off;            // residual buffer currently holding r (fuse 2 ping-pongs r / r1)
         for (int it = 0; it < cg_iters; ++it) {
@@ -458,13 +524,13 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
                 Fp.mode = 2; Fp.r = rcur; Fp.r_out = roth; Fp.p_out = poth; Fp.hp = s->hp + off; Fp.x_io = s->x + off;
                 Fp.scal = s->scal; Fp.beta_den = rr_out /* slot of the previous <r,r> */; Fp.rr_out = rr_in;
                 Fp.part = part; Fp.counter = counter; Fp.ctl = mask;
-                CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
+                CK(plan_forward(p, Fp, nodes, make_red(p, s->q, node0, nodes), st));
                 cur ^= 1; pcur = poth; rcur = roth;
             } else if (it > 0 && s->fuse_pupdate == 1) {
                 FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
                 Fp.mode = 1; Fp.r = s->r + off; Fp.p_out = poth; Fp.scal = s->scal; Fp.beta_num = rr_in; Fp.beta_den = rr_out;
                 Fp.ctl = mask;
-                CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
+                CK(plan_forward(p, Fp, nodes, make_red(p, s->q, node0, nodes), st));
                 cur ^= 1; pcur = poth;
             } else if (it > 0) {
                 CgParams U{};
@@ -475,17 +541,17 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
                 cur ^= 1; pcur = poth;
                 FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
                 Fp.ctl = mask;
-                CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
+                CK(plan_forward(p, Fp, nodes, make_red(p, s->q, node0, nodes), st));
             } else {
                 FwdParams Fp = make_fwd(p, pcur, s->stride, node0);
                 Fp.ctl = mask;
-                CK(launch_forward(Fp, nodes, p->max_chunks, make_red(p, s->q, node0, nodes), st));
+                CK(plan_forward(p, Fp, nodes, make_red(p, s->q, node0, nodes), st));
             }
             BackParams H = make_back(p, s->q, s->prec, s->hp + off, s->stride, node0);
             H.v = pcur; H.rhoD_vec = B.rhoD_vec; H.rhoD_s = s->rhoD_s; H.mu = s->mu;
             H.rvec = (s->fuse_pupdate == 2) ? rcur : nullptr;
             H.part = part; H.counter = counter; H.scal = s->scal; H.dot_slot = S_PHP; H.ctl = mask;
-            CK(launch_back(BACK_HP, H, nodes, st));
+            CK(plan_back(p, BACK_HP, H, nodes, st));
             SP.mode = 1; SP.rr_in = rr_in;
             CK(launch_sino_axpy(SP, st));
             const bool last = (it == cg_iters - 1);

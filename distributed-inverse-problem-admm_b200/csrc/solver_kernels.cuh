@@ -111,5 +111,9 @@ cudaError_t launch_edges(const EdgeParams& P, int nedges, int nblk, cudaStream_t
 cudaError_t launch_pack(const PackParams& P, int nitems, int narrow_blocks, cudaStream_t st);
 cudaError_t launch_finalize(const FinalizeParams& P, cudaStream_t st);
 cudaError_t launch_accept(const AcceptParams& P, cudaStream_t st);
+// dense-matrix operator (dense.cu): same contracts as launch_forward (mode 0 only) / launch_back
+cudaError_t launch_dense_forward(const float* A, const int* anode, const FwdParams& P, int nodes, const FwdReduceParams& R,
+                                 cudaStream_t st);
+cudaError_t launch_dense_back(const float* A, int mode, const BackParams& P, int nodes, cudaStream_t st);
 
 }  // namespace admm

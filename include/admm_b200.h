@@ -113,6 +113,13 @@ int admm_device_count(void); /* 0 when no CUDA device is visible (never throws) 
  * are the fp32-rounded trig values of every angle row (computed in fp64 on the host). */
 admm_plan* admm_plan_create(int N, int D, double det_w, int V, const int* ang_ptr, const float* cos32,
                             const float* sin32, int device);
+/* Dense-matrix plan: the reference's literal `A_dense_list[i]` ndarrays (block_2_load_odl_data.py:68-96; `Ai @ x`,
+ * `Ai.T @ r`, block_6_admm_loop_ver2.py:145,193), for tiny problems only (4 m_i n bytes per node).  `row_ptr[V+1]`:
+ * matrix-row range of every node; each matrix is (rows x N*N) float32 row-major, uploaded from the host once.  Every
+ * entry point below then works unchanged with D = 1 (a "sinogram" is the vector of a node's rows); admm_x_update
+ * needs fuse_pupdate = 0. */
+admm_plan* admm_plan_create_dense(int N, int V, const int* row_ptr, int device);
+int admm_plan_upload_dense(admm_plan* plan, int node, const float* h_A);
 void admm_plan_destroy(admm_plan* plan);
 #define ADMM_INFO_N 0
 #define ADMM_INFO_D 1

@@ -206,3 +206,53 @@ def test_block7_main_driver_end_to_end(tmp_path):
     snaps = sorted(p.name for p in (out / "snapshots").glob("iter_*_node_0.npy"))
     assert snaps and all(int(s.split("_")[1]) % 10 == 0 for s in snaps)          # snapshot_every = max_iters // 2
     assert len(x_list) == 5
+
+
+def test_dense_ndarray_operators_accepted_like_the_reference():
+    """The reference passes dense ndarrays in `A_dense_list` / `Ai` (block_6_admm_loop_ver2.py:26,145;
+    block_5_node_problem.py:8; block_3_graph_and_precisions.py:22).  SURVEY 8(b): still accepted for tiny N -- uploaded
+    and applied by plain dense kernels.  Same numbers as the matrix-free operators and as the oracle."""
+    import warnings
+    import block_3_graph_and_precisions as b3
+    from admm_b200 import DenseOperatorCUDA, RayTransformCUDA, node_angles
+    from block_5_node_problem import build_node_problem
+    from block_6_admm_loop_ver2 import decentralized_admm
+    from oracle import oracle as O
+    N, M, V, iters = 16, 24, 4, 12
+    thetas = node_angles(M, V)
+    img = O.shepp_logan(N)
+    ops_o = [O.JosephOperator(N, t) for t in thetas]
+    dense = [op.dense().astype(np.float32) for op in ops_o]                     # what the reference holds
+    sinos = [(op.forward(img) + 0.01 * np.random.default_rng(5 + i).standard_normal(op.shape[0]))
+             .reshape(op.nang, N).astype(np.float32) for i, op in enumerate(ops_o)]
+    G = O.make_graph("ring", V)
+    # the operator interface on a dense matrix
+    d0 = DenseOperatorCUDA(dense[0], N)
+    xv = np.random.default_rng(0).standard_normal(N * N)
+    assert d0.shape == dense[0].shape
+    assert _rel(d0 @ xv, dense[0].astype(np.float64) @ xv) < 1e-6
+    qv = np.random.default_rng(1).standard_normal(dense[0].shape[0])
+    assert _rel(d0.T @ qv, dense[0].astype(np.float64).T @ qv) < 1e-6
+    assert _rel(d0.colnorm2(), np.sum(dense[0].astype(np.float64) ** 2, axis=0)) < 1e-6
+    Wd, Qd = b3.make_precisions(dense, q_mode="arithmetic")                    # ndarray path of block_3:22
+    Wo, Qo = O.make_precisions([op.colnorm2() for op in ops_o], "arithmetic")
+    assert _rel(Wd[1], Wo[1]) < 1e-5
+    # the full loop on literal ndarrays
+    kw = dict(lam_tv=0.02, rho=2.0, max_iters=iters, eps_pri=0.0, eps_dual=0.0, phantom_true=img, verbose=False)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        xd, hd = decentralized_admm(dense, sinos, G, Wo, Qo, N, **kw)
+    assert any("dense operator" in str(m.message) for m in w)
+    xm, hm = decentralized_admm([RayTransformCUDA(N, t) for t in thetas], sinos, G, Wo, Qo, N, **kw)
+    xo, ho = O.decentralized_admm(ops_o, sinos, G, Wo, Qo, N, **{k: v for k, v in kw.items() if k != "verbose"})
+    assert np.allclose(hd["primal"], ho["primal"], rtol=1e-3) and np.allclose(hd["dual"], ho["dual"], rtol=1e-3)
+    assert np.allclose(hd["primal"], hm["primal"], rtol=1e-4) and np.array_equal(hd["tighten_history"], hm["tighten_history"])
+    for i in range(V):
+        assert _rel(xd[i], xo[i]) < 1e-3 and _rel(xd[i], xm[i]) < 1e-4
+    # block_5 with a dense Ai
+    xi, prob = build_node_problem(dense[2], sinos[2].reshape(-1), 2.0, [np.zeros(N * N)], N, 0.02, [np.ones(N * N)])
+    prob.solve(eps=1e-6, max_iters=200)
+    xr, pr = build_node_problem(RayTransformCUDA(N, thetas[2]), sinos[2].reshape(-1), 2.0, [np.zeros(N * N)], N, 0.02,
+                                [np.ones(N * N)])
+    pr.solve(eps=1e-6, max_iters=200)
+    assert _rel(xi.value, xr.value) < 1e-3 and abs(prob.value - pr.value) < 1e-3 * abs(pr.value)
