@@ -16,7 +16,6 @@ namespace admm {
 // (float4 loads / stores) and recomputes the (d - w') of its upper and left neighbours in registers, so there is
 // no shared-memory tile, no barrier before the reduction and every global access is a coalesced 16-byte one.
 constexpr int TVX = 32, TVY = 8;
-constexpr int TV_MIN_BLOCKS = 3;   // 79 registers, no spills (4 would cap at 64 registers and spill)
 
 struct Dw { float dwx, dwy, w1, w2; };
 
@@ -54,22 +53,16 @@ __device__ __forceinline__ void load_seg(const float* __restrict__ row, int c, i
     (void)vec;
 }
 
-__global__ void __launch_bounds__(TVX * TVY, TV_MIN_BLOCKS)
+__global__ void __launch_bounds__(TVX * TVY, 4)
 tv_fused_kernel(const TvParams P) {
     __shared__ __align__(16) float red[128];
-    // (d - w')_x and the unit-gradient x-component of every pixel of the block, for the row below; the y-components
-    // of each thread's last pixel, for the thread to its right: every pixel's shrink is evaluated ONCE (the block's
-    // first row and first column recompute their outside neighbour, 1/8 + 1/32 of the pixels)
-    __shared__ float s_dwx[TVY][TVX * 4], s_px[TVY][TVX * 4];
-    __shared__ float s_dwy[TVY][TVX], s_py[TVY][TVX];
     const int N = P.N;
     const int node = P.node0 + blockIdx.z;
-    if (P.masked && !P.ctl[node].active) return;   // a14 retry pass: this node was accepted already (block-uniform)
+    if (P.masked && !P.ctl[node].active) return;   // a14 retry pass: this node was accepted already
     const long long nb = (long long)blockIdx.z * P.stride;
     const long long n = (long long)N * N;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int r = blockIdx.y * TVY + ty;
-    const int c0 = (blockIdx.x * TVX + tx) * 4;
+    const int r = blockIdx.y * TVY + threadIdx.y;
+    const int c0 = (blockIdx.x * TVX + threadIdx.x) * 4;
     const float* __restrict__ x = P.x + nb;
     // device-side ping-pong parity of this node's multiplier (host parity when there is no control table): every block
     // reads it before it arrives at the grid-reduction counter, the last block flips it after all have arrived
@@ -80,28 +73,33 @@ tv_fused_kernel(const TvParams P) {
     float* __restrict__ wo2 = wo1 + n;
     const float kappa = P.lam / P.mu;
     float tv = 0.f, gn2 = 0.f, img = 0.f, rr = 0.f;
-    const bool live = (r < N && c0 < N);
-    const bool vec = ((N & 3) == 0);   // then c0 + 3 < N and rows are 16-byte aligned
-    const long long g0 = (long long)r * N + c0;
-    const bool up = r >= 1, dn = r + 1 < N;
-    const bool diag = (P.r != nullptr), upd = (P.r_upd != nullptr);
-    // what survives the barrier: (d - w') and the unit gradient of the own pixels, the Laplacian of the diagnostic
-    float dwx[4], dwy[4], pxo[4], pyo[4], lap[4];
-    float dwx_up[4] = {0.f, 0.f, 0.f, 0.f}, px_up[4] = {0.f, 0.f, 0.f, 0.f}, dwy_left = 0.f, py_left = 0.f;
-    if (live) {
-        float xc[6], xm[4];            // row r: c0-1 .. c0+4 ; row r-1: c0 .. c0+3
-        float xp[5], wc1[5], wc2[5];   // row r+1 and w of row r: c0-1 .. c0+3
+    if (r < N && c0 < N) {
+        const bool vec = ((N & 3) == 0);   // then c0 + 3 < N and rows are 16-byte aligned
+        const long long g0 = (long long)r * N + c0;
+        float xm[5], xc[6], xp[5], wc1[5], wc2[5], wu1[4], wu2[4];
+        const bool up = r >= 1, dn = r + 1 < N;
         if (vec) {
             const float4 q = ld4(x + g0);
             xc[1] = q.x; xc[2] = q.y; xc[3] = q.z; xc[4] = q.w;
             xc[0] = (c0 >= 1) ? x[g0 - 1] : 0.f;
             xc[5] = (c0 + 4 < N) ? x[g0 + 4] : 0.f;
-            if (up) { const float4 a = ld4(x + g0 - N); xm[0] = a.x; xm[1] = a.y; xm[2] = a.z; xm[3] = a.w; }
-            else { xm[0] = xm[1] = xm[2] = xm[3] = 0.f; }
+            if (up) {
+                const float4 a = ld4(x + g0 - N);
+                xm[0] = a.x; xm[1] = a.y; xm[2] = a.z; xm[3] = a.w;
+                xm[4] = (c0 + 4 < N) ? x[g0 - N + 4] : 0.f;
+                const float4 u1 = ld4(w1p + g0 - N), u2 = ld4(w2p + g0 - N);
+                wu1[0] = u1.x; wu1[1] = u1.y; wu1[2] = u1.z; wu1[3] = u1.w;
+                wu2[0] = u2.x; wu2[1] = u2.y; wu2[2] = u2.z; wu2[3] = u2.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) xm[k] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { wu1[k] = 0.f; wu2[k] = 0.f; }
+            }
             if (dn) {
                 const float4 a = ld4(x + g0 + N);
                 xp[1] = a.x; xp[2] = a.y; xp[3] = a.z; xp[4] = a.w;
-                xp[0] = (tx == 0 && c0 >= 1) ? x[g0 + N - 1] : 0.f;
+                xp[0] = (c0 >= 1) ? x[g0 + N - 1] : 0.f;
             } else {
 #pragma unroll
                 for (int k = 0; k < 5; ++k) xp[k] = 0.f;
@@ -109,126 +107,86 @@ tv_fused_kernel(const TvParams P) {
             const float4 a1 = ld4(w1p + g0), a2 = ld4(w2p + g0);
             wc1[1] = a1.x; wc1[2] = a1.y; wc1[3] = a1.z; wc1[4] = a1.w;
             wc2[1] = a2.x; wc2[2] = a2.y; wc2[3] = a2.z; wc2[4] = a2.w;
-            wc1[0] = (tx == 0 && c0 >= 1) ? w1p[g0 - 1] : 0.f;
-            wc2[0] = (tx == 0 && c0 >= 1) ? w2p[g0 - 1] : 0.f;
+            wc1[0] = (c0 >= 1) ? w1p[g0 - 1] : 0.f;
+            wc2[0] = (c0 >= 1) ? w2p[g0 - 1] : 0.f;
         } else {
-            float xm5[5];
             load_seg<6>(x + (long long)r * N, c0 - 1, N, true, false, xc);
-            load_seg<5>(x + (long long)(r - 1) * N, c0, N, up, false, xm5);
-            xm[0] = xm5[0]; xm[1] = xm5[1]; xm[2] = xm5[2]; xm[3] = xm5[3];
+            load_seg<5>(x + (long long)(r - 1) * N, c0, N, up, false, xm);
             load_seg<5>(x + (long long)(r + 1) * N, c0 - 1, N, dn, false, xp);
             load_seg<5>(w1p + (long long)r * N, c0 - 1, N, true, false, wc1);
             load_seg<5>(w2p + (long long)r * N, c0 - 1, N, true, false, wc2);
+            load_seg<4>(w1p + (long long)(r - 1) * N, c0, N, up, false, wu1);
+            load_seg<4>(w2p + (long long)(r - 1) * N, c0, N, up, false, wu2);
         }
-        // ---- this thread's four pixels -----------------------------------------------------------------------
-        float w1o[4], w2o[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = c0 + k;
-            const bool rt = c + 1 < N, lf = c >= 1;
-            const float xcv = xc[k + 1];
-            const float gx = dn ? xp[k + 1] - xcv : 0.f;
-            const float gy = rt ? xc[k + 2] - xcv : 0.f;
-            const Dw o = shrink_dw(gx, gy, wc1[k + 1], wc2[k + 1], kappa);
-            dwx[k] = o.dwx; dwy[k] = o.dwy; w1o[k] = o.w1; w2o[k] = o.w2;
-            float mg;
-            unit_grad(gx, gy, pxo[k], pyo[k], mg);
-            float l = 0.f;
-            if (up) l += xcv - xm[k];
-            if (dn) l += xcv - xp[k + 1];
-            if (lf) l += xcv - xc[k];
-            if (rt) l += xcv - xc[k + 2];
-            lap[k] = l;
-            if (c < N) {
-                tv += mg;
-                if (P.xtrue) { const float e = xcv - P.xtrue[g0 + k]; img = fmaf(e, e, img); }
-            }
-            s_dwx[ty][tx * 4 + k] = dwx[k];
-            s_px[ty][tx * 4 + k] = pxo[k];
-        }
-        s_dwy[ty][tx] = dwy[3];
-        s_py[ty][tx] = pyo[3];
-        if (vec) {
-            st4(wo1 + g0, make_float4(w1o[0], w1o[1], w1o[2], w1o[3]));
-            st4(wo2 + g0, make_float4(w2o[0], w2o[1], w2o[2], w2o[3]));
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (c0 + k < N) { wo1[g0 + k] = w1o[k]; wo2[g0 + k] = w2o[k]; }
-        }
-        // ---- neighbours outside the block: recompute (same arithmetic as their owner) ---------------------------
-        if (ty == 0 && up) {
-            float wu1[4], wu2[4], xm4 = 0.f;
-            if (vec) {
-                const float4 u1 = ld4(w1p + g0 - N), u2 = ld4(w2p + g0 - N);
-                wu1[0] = u1.x; wu1[1] = u1.y; wu1[2] = u1.z; wu1[3] = u1.w;
-                wu2[0] = u2.x; wu2[1] = u2.y; wu2[2] = u2.z; wu2[3] = u2.w;
-                xm4 = (c0 + 4 < N) ? x[g0 - N + 4] : 0.f;
-            } else {
-                load_seg<4>(w1p + (long long)(r - 1) * N, c0, N, true, false, wu1);
-                load_seg<4>(w2p + (long long)(r - 1) * N, c0, N, true, false, wu2);
-                xm4 = (c0 + 4 < N) ? x[(long long)(r - 1) * N + c0 + 4] : 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const bool rt = c0 + k + 1 < N;
-                const float xr = (k < 3) ? xm[k + 1] : xm4;
-                const float gxu = xc[k + 1] - xm[k], gyu = rt ? xr - xm[k] : 0.f;
-                dwx_up[k] = shrink_dw(gxu, gyu, wu1[k], wu2[k], kappa).dwx;
-                float pyu, mg;
-                unit_grad(gxu, gyu, px_up[k], pyu, mg);
-            }
-        }
-        if (tx == 0 && c0 >= 1) {
+        // left neighbour (r, c0-1): only its y-component of (d - w') and of the unit gradient is needed
+        float dwy_prev = 0.f, py_prev = 0.f;
+        if (c0 >= 1) {
             const float gx = dn ? xp[0] - xc[0] : 0.f, gy = xc[1] - xc[0];
-            dwy_left = shrink_dw(gx, gy, wc1[0], wc2[0], kappa).dwy;
+            dwy_prev = shrink_dw(gx, gy, wc1[0], wc2[0], kappa).dwy;
             float pxl, mg;
-            unit_grad(gx, gy, pxl, py_left, mg);
+            unit_grad(gx, gy, pxl, py_prev, mg);
         }
-    }
-    __syncthreads();
-    if (live) {
-        if (ty > 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { dwx_up[k] = s_dwx[ty - 1][tx * 4 + k]; px_up[k] = s_px[ty - 1][tx * 4 + k]; }
-        }
-        if (tx > 0) { dwy_left = s_dwy[ty][tx - 1]; py_left = s_py[ty][tx - 1]; }
-        float told[4], rc[4] = {0.f, 0.f, 0.f, 0.f};
+        float w1o[4], w2o[4], tvo[4];
+        float told[4], rc[4], xt[4];
+        const bool diag = (P.r != nullptr);
+        const bool upd = (P.r_upd != nullptr);
         const float* rsrc = upd ? P.r_upd : P.r;
         float* __restrict__ tvt = P.tvterm + nb;
         if (vec) {
             const float4 t4 = ld4(tvt + g0);
             told[0] = t4.x; told[1] = t4.y; told[2] = t4.z; told[3] = t4.w;
             if (diag || upd) { const float4 q = ld4(rsrc + nb + g0); rc[0] = q.x; rc[1] = q.y; rc[2] = q.z; rc[3] = q.w; }
+            if (P.xtrue) { const float4 q = ld4(P.xtrue + g0); xt[0] = q.x; xt[1] = q.y; xt[2] = q.z; xt[3] = q.w; }
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const bool ok = c0 + k < N;
                 told[k] = ok ? tvt[g0 + k] : 0.f;
                 rc[k] = (ok && (diag || upd)) ? rsrc[nb + g0 + k] : 0.f;
+                xt[k] = (ok && P.xtrue) ? P.xtrue[g0 + k] : 0.f;
             }
         }
-        float tvo[4];
-        float dwy_prev = dwy_left, py_prev = py_left;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = c0 + k;
             const bool ok = c < N, rt = c + 1 < N, lf = c >= 1;
-            float kt = up ? dwx_up[k] : 0.f;
-            if (dn) kt -= dwx[k];
-            if (lf) kt += dwy_prev;
-            if (rt) kt -= dwy[k];
-            if (ok && diag) {
-                float dv = 0.f;   // block_4_tv_helpers.py:25-35 as shipped (-div, sign-flipped border)
-                if (N >= 2) {
-                    if (r == 0) dv += pxo[k]; else if (!dn) dv -= px_up[k]; else dv += px_up[k] - pxo[k];
-                    if (c == 0) dv += pyo[k]; else if (!rt) dv -= py_prev; else dv += py_prev - pyo[k];
-                }
-                const float gv = told[k] - rc[k] - P.mu * lap[k] + P.lam * dv;
-                gn2 = fmaf(gv, gv, gn2);
+            const float xcv = xc[k + 1];
+            const float gx = dn ? xp[k + 1] - xcv : 0.f;
+            const float gy = rt ? xc[k + 2] - xcv : 0.f;
+            const Dw o = shrink_dw(gx, gy, wc1[k + 1], wc2[k + 1], kappa);
+            float dwx_up = 0.f, px_up = 0.f;
+            if (up) {
+                const float gxu = xcv - xm[k], gyu = rt ? xm[k + 1] - xm[k] : 0.f;
+                dwx_up = shrink_dw(gxu, gyu, wu1[k], wu2[k], kappa).dwx;
+                float pyu, mg;
+                unit_grad(gxu, gyu, px_up, pyu, mg);
             }
-            tvo[k] = P.mu * kt;
-            dwy_prev = dwy[k]; py_prev = pyo[k];
+            float kt = dwx_up;
+            if (dn) kt -= o.dwx;
+            if (lf) kt += dwy_prev;
+            if (rt) kt -= o.dwy;
+            float pxo, pyo, mag;
+            unit_grad(gx, gy, pxo, pyo, mag);
+            if (ok) {
+                tv += mag;
+                if (diag) {
+                    float lap = 0.f;
+                    if (up) lap += xcv - xm[k];
+                    if (dn) lap += xcv - xp[k + 1];
+                    if (lf) lap += xcv - xc[k];
+                    if (rt) lap += xcv - xc[k + 2];
+                    float dv = 0.f;   // block_4_tv_helpers.py:25-35 as shipped (-div, sign-flipped border)
+                    if (N >= 2) {
+                        if (r == 0) dv += pxo; else if (!dn) dv -= px_up; else dv += px_up - pxo;
+                        if (c == 0) dv += pyo; else if (!rt) dv -= py_prev; else dv += py_prev - pyo;
+                    }
+                    const float gv = told[k] - rc[k] - P.mu * lap + P.lam * dv;
+                    gn2 = fmaf(gv, gv, gn2);
+                }
+                if (P.xtrue) { const float e = xcv - xt[k]; img = fmaf(e, e, img); }
+            }
+            w1o[k] = o.w1; w2o[k] = o.w2; tvo[k] = P.mu * kt;
+            dwy_prev = o.dwy; py_prev = pyo;
         }
         float rn[4];   // residual of the NEXT solve: r + (tvterm' - tvterm)
 #pragma unroll
@@ -237,6 +195,8 @@ tv_fused_kernel(const TvParams P) {
             if (upd && c0 + k < N) rr = fmaf(rn[k], rn[k], rr);
         }
         if (vec) {
+            st4(wo1 + g0, make_float4(w1o[0], w1o[1], w1o[2], w1o[3]));
+            st4(wo2 + g0, make_float4(w2o[0], w2o[1], w2o[2], w2o[3]));
             st4(tvt + g0, make_float4(tvo[0], tvo[1], tvo[2], tvo[3]));
             if (upd) {
                 st4(P.r_upd + nb + g0, make_float4(rn[0], rn[1], rn[2], rn[3]));
@@ -246,7 +206,7 @@ tv_fused_kernel(const TvParams P) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (c0 + k < N) {
-                    tvt[g0 + k] = tvo[k];
+                    wo1[g0 + k] = w1o[k]; wo2[g0 + k] = w2o[k]; tvt[g0 + k] = tvo[k];
                     if (upd) { P.r_upd[nb + g0 + k] = rn[k]; P.p_out[nb + g0 + k] = rn[k]; }
                 }
         }
@@ -255,14 +215,14 @@ tv_fused_kernel(const TvParams P) {
     block_sum<4>(v, red);
     const int nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
     __shared__ int s_slots[4];
-    if (tx == 0 && ty == 0) {
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
         s_slots[0] = S_TV; s_slots[1] = S_GN2; s_slots[2] = S_IMG;
         s_slots[3] = P.r_upd ? S_RR0 : S_SCRATCH;
     }
     // (s_slots is ordered before its use by the barriers inside grid_reduce_store)
     const bool last = grid_reduce_store<4>(v, P.part + (long long)blockIdx.z * nblk * 4, P.counter + blockIdx.z, blk,
                                            nblk, P.scal + (long long)node * NSCAL, red, s_slots);
-    if (last && P.ctl && tx == 0 && ty == 0) P.ctl[node].wpar ^= 1;
+    if (last && P.ctl && threadIdx.x == 0 && threadIdx.y == 0) P.ctl[node].wpar ^= 1;
 }
 
 // =================================================================================================
