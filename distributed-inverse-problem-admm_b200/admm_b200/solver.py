@@ -46,7 +46,7 @@ class ADMMEngine:
                  node_prec=None, tv_mu=None, tv_sweeps=1, cg_iters=2, phantom_true=None, weighted_z=False,
                  device=0, dist=None, rank=0, world=1, group=None, node_group=None, fuse_pupdate=True,
                  max_iters=200, ax_refresh_every=10, exchange="auto", exchange_phases=None, partition="auto",
-                 acceptance=False, max_tighten=2, carry_residual="iteration", cuda_graph="auto"):
+                 acceptance=False, max_tighten=2, carry_residual=False, cuda_graph="auto"):
         torch = _torch()
         nat.require_cuda()
         self.torch = torch
@@ -59,11 +59,12 @@ class ADMMEngine:
         self.S, self.C = int(tv_sweeps), int(cg_iters)
         # a14 accept / tighten-and-retry rule (block_6_admm_loop_ver2.py:100-176), decided on the device
         self.acceptance, self.max_tighten = bool(acceptance), int(max_tighten)
-        # CG residual between solves: "iteration" (default): the first solve of an outer iteration rebuilds r = rhs0 +
-        # tvterm - H x with a back-projection, later sweeps / a14 retry solves of the SAME iteration take the r the TV
-        # pass carried along (r += tvterm' - tvterm) -- at most max_tighten incremental steps, no drift across
-        # iterations; "always": also across iterations (rhs0 assembly carries it; rebuilt every ax_refresh_every
-        # iterations; measured: 200-iteration trace error grows from 4e-6 to 2e-4..6e-3); False: rebuild at every solve
+        # CG residual between solves.  False (default): every solve rebuilds r = rhs0 + tvterm - H x with a
+        # back-projection.  "iteration": only the first solve of an outer iteration does, later sweeps / a14 retry solves
+        # take the r the TV pass carried along (r += tvterm' - tvterm); "always": also across iterations (the rhs0
+        # assembly carries it; rebuilt every ax_refresh_every iterations).  Carrying saves 1.7 ms per solve at cfg 4 but
+        # keeps the fp32 CG-recurrence residual instead of the true one: measured 200-iteration trace error vs the
+        # oracle 1e-3 ("iteration") and 2e-4..6e-3 ("always") instead of 4e-6 -- at north_star's tolerance, so off
         if carry_residual not in ("iteration", "always", False, None):
             raise ValueError(f"carry_residual must be 'iteration', 'always' or False, not {carry_residual!r}")
         self.carry_r = carry_residual or False
@@ -188,6 +189,9 @@ class ADMMEngine:
         # the outer iteration as a CUDA graph (single GPU): ~15 C-ABI calls / 20-60 launches per iteration replay as
         # one submission -- what makes the small, launch-bound configs (cfg 1, 2, 5) run at kernel speed
         self.use_graph = ((self.world == 1) if cuda_graph == "auto" else bool(cuda_graph)) and not self.dense
+        import os
+        if os.environ.get("ADMM_B200_NOGRAPH") == "1":     # diagnostics: always launch eagerly
+            self.use_graph = False
         self._graphs = {}
         self.replayed_launches = 0     # kernels launched through graph replays (the library's own counter sees only eager launches)
         self.W = None

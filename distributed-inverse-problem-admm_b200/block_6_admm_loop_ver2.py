@@ -62,7 +62,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                        cg_iters=2, tv_sweeps=1, tv_mu=None, node_prec=None, weighted_z=False, scs_eps=None,
                        check_every=1, node_group=None, fuse_pupdate=True, device=None, return_engine=False,
                        distributed=None, ax_refresh_every=10, exchange="auto", gather="all", exchange_phases=None, partition="auto",
-                       acceptance=True, max_tighten=2, carry_residual="iteration",
+                       acceptance=True, max_tighten=2, carry_residual=False,
                        **kwargs):
     """Returns x_per_node as list of reconstructions, each length n, and the history of residual norms
     (block_6_admm_loop_ver2.py:21-24).
