@@ -54,7 +54,8 @@ class State(ctypes.Structure):
         ("q_uniform", ctypes.c_float), ("w_parity", ctypes.c_int), ("fuse_pupdate", ctypes.c_int),
         ("defer_tv", ctypes.c_int), ("reuse_ax", ctypes.c_int), ("ctl", ctypes.c_void_p), ("masked", ctypes.c_int),
         ("carry_r", ctypes.c_int), ("reuse_r", ctypes.c_int), ("iter_dev", ctypes.c_void_p),
-        ("hist_stride", ctypes.c_longlong)]
+        ("hist_stride", ctypes.c_longlong), ("accept_mode", ctypes.c_int), ("max_tighten", ctypes.c_int),
+        ("eps_target", ctypes.c_double), ("skip_mse", ctypes.c_int)]
 
 
 EDGE_FIELDS = ("xi", "xj", "yi", "yj", "z", "ai", "aj", "Wi", "Wj", "qij", "qji")  # struct admm_edge (u64 each)

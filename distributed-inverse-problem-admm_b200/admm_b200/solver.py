@@ -411,8 +411,11 @@ class ADMMEngine:
         st.rho, st.lam, st.mu, st.q_uniform = self.rho, self.lam, self.mu, self.q_uniform
         st.w_parity = 0
         st.fuse_pupdate = int(fuse) if not isinstance(fuse, bool) else (2 if fuse else 0)
-        # the a14 decision needs |g| of the TV pass before x is final, so nothing can be deferred behind the exchange
+        # sharded runs hold the last TV pass back so that the cut-edge exchange starts as soon as x is final.  With the
+        # a14 rule only the LAST retry solve's TV pass can be held back (the earlier ones feed the decisions)
         st.defer_tv = 1 if (self.world > 1 and not self.acceptance) else 0
+        self._defer_last_tv = (self.world > 1 and self.acceptance and self.max_tighten >= 1 and self.phases == 1
+                               and self.node_group >= self.V)
 
     def _stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
@@ -437,18 +440,27 @@ class ADMMEngine:
         for ph in range(self.phases):
             for n0 in range(bounds[ph], bounds[ph + 1], self.node_group):
                 nn = min(self.node_group, bounds[ph + 1] - n0)
+                if not self.acceptance:
+                    nat.check(L.admm_x_update(h, sref, n0, nn, self.S, self.C, self._stream()), "admm_x_update")
+                    continue
+                # :155-176 on the device: nodes whose |g| misses the target are solved again (warm start, masked launches),
+                # at most max_tighten times; no host round trip.  The decision itself is taken inside the TV pass that
+                # ends each solve (by the last block of every node), |A x - b|^2 is refreshed by the last solve only
+                st.max_tighten, st.eps_target = self.max_tighten, eps_target
+                st.accept_mode, st.skip_mse = 1, (1 if self.max_tighten > 0 else 0)
                 nat.check(L.admm_x_update(h, sref, n0, nn, self.S, self.C, self._stream()), "admm_x_update")
-                if self.acceptance:
-                    # :155-176 on the device: nodes whose |g| misses the target are solved again (warm start, masked
-                    # launches), at most max_tighten times; no host round trip
-                    nat.check(L.admm_accept(h, sref, n0, nn, eps_target, self.max_tighten, 1, self._stream()), "admm_accept")
-                    keep = (st.reuse_ax, st.reuse_r)
-                    st.masked, st.reuse_ax, st.reuse_r = 1, 1, st.carry_r
-                    for _ in range(self.max_tighten):
-                        nat.check(L.admm_x_update(h, sref, n0, nn, self.S, self.C, self._stream()), "admm_x_update")
-                        nat.check(L.admm_accept(h, sref, n0, nn, eps_target, self.max_tighten, 0, self._stream()),
-                                  "admm_accept")
-                    st.masked, st.reuse_ax, st.reuse_r = 0, keep[0], keep[1]
+                keep = (st.reuse_ax, st.reuse_r)
+                st.masked, st.reuse_ax, st.reuse_r, st.accept_mode = 1, 1, st.carry_r, 2
+                for t in range(self.max_tighten):
+                    last = (t == self.max_tighten - 1)
+                    # sharded: x is final after the LAST retry's CG, so its TV pass (w, tvterm, |g| only) is held back and
+                    # runs under the cut-edge exchange (tv_phase); needs the whole rank in one node group
+                    st.defer_tv = 1 if (self._defer_last_tv and last) else 0
+                    st.skip_mse = 0 if last else 1
+                    nat.check(L.admm_x_update(h, sref, n0, nn, self.S, self.C, self._stream()), "admm_x_update")
+                if not self._defer_last_tv:
+                    st.masked, st.accept_mode = 0, 0
+                st.reuse_ax, st.reuse_r, st.skip_mse = keep[0], keep[1], 0
             if self.phases > 1:
                 if ph == self.phases - 1 and getattr(self, "time_exchange", False):
                     self._ex_t0 = self.torch.cuda.Event(enable_timing=True)
@@ -457,9 +469,15 @@ class ADMMEngine:
         return reqs
 
     def tv_phase(self):
-        """The deferred last TV pass (K3) of every local node."""
+        """The deferred last TV pass (K3) of every local node (with the a14 rule: of the nodes still active in the last
+        retry solve, followed by the final acceptance bookkeeping)."""
         st = self.st
-        nat.check(nat.lib().admm_tv_pass(self.plan.handle, ctypes.byref(st), 0, self.V, 1, self._stream()), "admm_tv_pass")
+        L, h, sref = nat.lib(), self.plan.handle, ctypes.byref(self.st)
+        if self.acceptance:     # masked pass of the last retry solve; carries that solve's a14 bookkeeping (accept_mode 2)
+            nat.check(L.admm_tv_pass(h, sref, 0, self.V, 1, self._stream()), "admm_tv_pass")
+            st.masked, st.defer_tv, st.accept_mode = 0, 0, 0
+            return
+        nat.check(L.admm_tv_pass(h, sref, 0, self.V, 1, self._stream()), "admm_tv_pass")
 
     def exchange_start(self, phase=None):
         """Pack a = x + y of this rank's cut-edge ends (of exchange phase `phase`, or all).  NCCL mode: post the grouped
@@ -556,7 +574,7 @@ class ADMMEngine:
                     self._ex_t0 = self.torch.cuda.Event(enable_timing=True)
                     self._ex_t0.record()
                 reqs = self.exchange_start()  # x is final: the exchange runs under the TV pass and the local edges
-            if self.st.defer_tv:
+            if self.st.defer_tv or self._defer_last_tv:
                 self.tv_phase()
             if timed:
                 self._edges_timed = (self._ex_t0, self.torch.cuda.Event(enable_timing=True))

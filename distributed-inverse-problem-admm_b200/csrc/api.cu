@@ -466,13 +466,17 @@ static TvParams make_tv(const admm_plan* p, const admm_state* s, int node0, bool
     T.part = s->part + (long long)node0 * admm_plan_info(p, ADMM_INFO_PART_FLOATS);
     T.counter = s->counter + node0; T.scal = s->scal;
     T.ctl = reinterpret_cast<NodeCtl*>(s->ctl); T.masked = (s->ctl && s->masked) ? 1 : 0;
+    T.accept = 0;   // set by the caller for the pass that ends a solve
+    T.max_tighten = s->max_tighten; T.eps_target2 = s->eps_target * s->eps_target; T.iter_dev = s->iter_dev;
     return T;
 }
 
 extern "C" int admm_tv_pass(admm_plan* p, admm_state* s, int node0, int nodes, int with_diag, void* stream) {
     if (int e = check_nodes(p, node0, nodes)) return e;
     if (!s) return fail(ADMM_ERR_ARG, "admm_tv_pass: null state");
-    CK(launch_tv(make_tv(p, s, node0, with_diag != 0, s->w_parity), nodes, (cudaStream_t)stream));
+    TvParams T = make_tv(p, s, node0, with_diag != 0, s->w_parity);
+    if (s->ctl && with_diag) T.accept = s->accept_mode;   // a deferred pass that ends a solve carries the a14 decision
+    CK(launch_tv(T, nodes, (cudaStream_t)stream));
     return ADMM_OK;
 }
 
@@ -568,11 +572,13 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
             }
         }
         if (!(s->defer_tv && sw == sweeps - 1)) {
-            CK(launch_tv(make_tv(p, s, node0, true, parity), nodes, st));
+            TvParams T = make_tv(p, s, node0, true, parity);
+            if (s->ctl && sw == sweeps - 1) T.accept = s->accept_mode;   // the a14 decision rides on the solve's last TV pass
+            CK(launch_tv(T, nodes, st));
             parity ^= 1;
         }
     }
-    CK(launch_sino_resid(SP, nodes, st));
+    if (!s->skip_mse) CK(launch_sino_resid(SP, nodes, st));
     return ADMM_OK;
 }
 

@@ -17,6 +17,25 @@ namespace admm {
 // no shared-memory tile, no barrier before the reduction and every global access is a coalesced 16-byte one.
 constexpr int TVX = 32, TVY = 8;
 
+// one node's a14 decision (block_6_admm_loop_ver2.py:155-176): accepted if |g| <= eps_target (:155) or the tighten cap is
+// reached (:164), else one more try (:175)
+__device__ __forceinline__ void accept_node(NodeCtl* ctl, double gn2, bool first, int max_tighten, double tgt2,
+                                            const int* iter_dev) {
+    NodeCtl c = *ctl;
+    if (first) { c.active = 1; c.tries = 0; }
+    if (iter_dev) {   // eps_target = 2 / (k+1)^1.005 from the device's own iteration counter (:101-103)
+        const double t = 2.0 / pow((double)(*iter_dev + 1), 1.005);
+        tgt2 = t * t;
+    }
+    if (c.active) {
+        if (gn2 <= tgt2 || c.tries >= max_tighten) c.active = 0;
+        else c.tries += 1;
+    }
+    ctl->active = c.active;
+    ctl->tries = c.tries;
+}
+
+
 struct Dw { float dwx, dwy, w1, w2; };
 
 __device__ __forceinline__ Dw shrink_dw(float gx, float gy, float w1, float w2, float kappa) {
@@ -222,7 +241,13 @@ tv_fused_kernel(const TvParams P) {
     // (s_slots is ordered before its use by the barriers inside grid_reduce_store)
     const bool last = grid_reduce_store<4>(v, P.part + (long long)blockIdx.z * nblk * 4, P.counter + blockIdx.z, blk,
                                            nblk, P.scal + (long long)node * NSCAL, red, s_slots);
-    if (last && P.ctl && threadIdx.x == 0 && threadIdx.y == 0) P.ctl[node].wpar ^= 1;
+    if (last && P.ctl && threadIdx.x == 0 && threadIdx.y == 0) {
+        P.ctl[node].wpar ^= 1;
+        // the a14 decision of this node, taken here instead of by a separate launch (thread 0 stored |g|^2 itself)
+        if (P.accept)
+            accept_node(P.ctl + node, P.scal[(long long)node * NSCAL + S_GN2], P.accept == 1, P.max_tighten,
+                        P.eps_target2, P.iter_dev);
+    }
 }
 
 // =================================================================================================
@@ -563,20 +588,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams P) {
 __global__ void __launch_bounds__(128) accept_kernel(const AcceptParams P) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= P.nodes) return;
-    NodeCtl c = P.ctl[P.node0 + v];
-    if (P.first) { c.active = 1; c.tries = 0; }
-    double tgt2 = P.eps_target2;
-    if (P.iter_dev) {   // eps_target = 2 / (k+1)^1.005 from the device's own iteration counter (:101-103)
-        const double t = 2.0 / pow((double)(*P.iter_dev + 1), 1.005);
-        tgt2 = t * t;
-    }
-    if (c.active) {
-        const double gn2 = P.scal[(long long)(P.node0 + v) * NSCAL + S_GN2];
-        if (gn2 <= tgt2 || c.tries >= P.max_tighten) c.active = 0;
-        else c.tries += 1;
-    }
-    P.ctl[P.node0 + v].active = c.active;
-    P.ctl[P.node0 + v].tries = c.tries;
+    accept_node(P.ctl + P.node0 + v, P.scal[(long long)(P.node0 + v) * NSCAL + S_GN2], P.first != 0, P.max_tighten,
+                P.eps_target2, P.iter_dev);
 }
 
 // ---- launchers --------------------------------------------------------------------------------------

@@ -20,6 +20,11 @@ struct TvParams {
     float* part; unsigned* counter; double* scal;
     NodeCtl* ctl;          // per-node w parity (flipped here) / active mask; nullptr: host parity, all nodes
     int masked;            // 1: skip nodes with ctl[node].active == 0
+    // a14 decision folded into this pass (taken by the last block of each node, right after |g|^2 is reduced):
+    // 0: none ; 1: decision after the iteration's first solve ; 2: after a retry solve
+    int accept, max_tighten;
+    double eps_target2;
+    const int* iter_dev;
 };
 
 struct CgParams {

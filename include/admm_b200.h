@@ -87,6 +87,11 @@ typedef struct admm_state {
                                  eps_target = 2/(k+1)^1.005 from it on the device, and admm_finalize treats d_row as the
                                  base of the history, writes row k at d_row + k*hist_stride and increments k          */
     long long hist_stride;    /* doubles between history rows (with iter_dev)                                          */
+    int accept_mode;          /* a14 decision folded into the TV pass that ends a solve (no separate launch): 0 none,
+                                 1 decision after the iteration's first solve, 2 after a retry solve (see admm_accept)  */
+    int max_tighten;          /* retry cap of that decision (block_6_admm_loop_ver2.py:113: 2)                           */
+    double eps_target;        /* its target when iter_dev is NULL                                                       */
+    int skip_mse;             /* 1: admm_x_update does not refresh |A x - b|^2 (only the iteration's last solve needs to) */
 } admm_state;
 
 /* Per-node control word (block_6_admm_loop_ver2.py:110-113 `accepted`, `tighten_tries`): zero-initialised by the
