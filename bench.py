@@ -317,7 +317,7 @@ def main():
     ap.add_argument("--node-group", type=int, default=0)
     ap.add_argument("--slices", type=int, default=0, help="override the slice count of cfg5")
     ap.add_argument("--no-fuse", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "push", "nccl"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "owner", "p2p", "push", "nccl"])
     ap.add_argument("--partition", default="auto", choices=["auto", "mincut", "contiguous"],
                     help="node -> GPU map when sharded (auto: balanced min-cut for <= 256 nodes)")
     ap.add_argument("--exchange-phases", type=int, default=None,
@@ -370,7 +370,9 @@ def main():
                      max_iters=total, exchange=args.exchange, exchange_phases=args.exchange_phases, partition=args.partition,
                      acceptance=bool(args.acceptance), carry_residual=(False if args.carry == 'off' else args.carry))
 
-    args.exchange_used = "push" if (eng.exchange_mode == "p2p" and getattr(eng, "_push", False)) else eng.exchange_mode
+    args.exchange_used = ("single-owner (peer memory: x pushed to the edge's owner, v = z' - y' stored back by its edge kernel)"
+                          if getattr(eng, "_owner", False) else
+                          "push" if (eng.exchange_mode == "p2p" and getattr(eng, "_push", False)) else eng.exchange_mode)
     args.phases_used = eng.phases
     if world > 1:
         from admm_b200.sharding import cut_statistics

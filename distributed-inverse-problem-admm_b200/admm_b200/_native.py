@@ -58,7 +58,7 @@ class State(ctypes.Structure):
         ("eps_target", ctypes.c_double), ("skip_mse", ctypes.c_int)]
 
 
-EDGE_FIELDS = ("xi", "xj", "yi", "yj", "z", "ai", "aj", "Wi", "Wj", "qij", "qji")  # struct admm_edge (u64 each)
+EDGE_FIELDS = ("xi", "xj", "yi", "yj", "z", "ai", "aj", "Wi", "Wj", "qij", "qji", "vi", "vj")  # struct admm_edge (u64 each)
 PACK_FIELDS = ("x", "y", "out")                                                    # struct admm_pack_item
 
 _lib = None

@@ -29,6 +29,7 @@ class LocalEdge:
     sslot: int = -1   # row of this rank's a in send[peer]  (ordered by the phase of the LOCAL end's node)
     rslot: int = -1   # row of the peer's a in recv[peer]     (ordered by the phase of the REMOTE end's node)
     sphase: int = 0   # exchange phase in which this rank's end is sent
+    owner: int = -1   # rank that computes the edge update in the single-owner exchange (local edges: this rank)
 
 
 @dataclass
@@ -216,6 +217,23 @@ def build_shard_plan(G, world: int, rank: int, phases: int = 1, node_rank=None) 
             exch.setdefault(le.peer, []).append(e)
         sp.eslot[e] = le.slot
         sp.local_edges.append(le)
+    # single-owner exchange: every cut edge is updated by ONE of its two ranks.  Deterministic greedy balance, the same
+    # on every rank: starting from each rank's count of local edges, cut edges in G.edges() order go to the end whose
+    # rank has fewer edges to update so far (tie: the min end's rank)
+    owned = [0] * world
+    owner_of = {}
+    for e, (i, j) in enumerate(edges):
+        if nr[int(i)] == nr[int(j)]:
+            owner_of[e] = nr[int(i)]
+            owned[nr[int(i)]] += 1
+    for e, (i, j) in enumerate(edges):
+        ri, rj = nr[int(i)], nr[int(j)]
+        if ri != rj:
+            o = ri if owned[ri] <= owned[rj] else rj
+            owner_of[e] = o
+            owned[o] += 1
+    for le in sp.local_edges:
+        le.owner = owner_of[le.e]
     sp.peers = sorted(exch)
     sp.exch = {p: sorted(exch[p]) for p in sp.peers}
     sp.phases, sp.node_phase = phases, node_phase

@@ -74,8 +74,12 @@ class ADMMEngine:
         # block's x-update).  Peer-memory exchange: nothing to post early -- the consumer reads the remote buffer.
         # (measured on 2 and 8 B200s: splitting the x-updates into two blocks costs more in short-kernel tails than the
         # earlier transfer hides, so the default is one phase -- profiles/README.md)
-        if exchange not in ("auto", "p2p", "push", "nccl"):
+        if exchange not in ("auto", "owner", "p2p", "push", "nccl"):
             raise ValueError(f"unknown exchange mode {exchange!r}")
+        # single-owner exchange ("owner", the default when sharded): every cut edge is updated by ONE of its two ranks
+        # (balanced, sharding.build_shard_plan); the other rank stores x of its end into the owner's buffer before the
+        # edge pass and gets v = z' - y' back, written by the owner's edge kernel straight into its buffer
+        self._owner = (self.world > 1 and exchange in ("auto", "owner"))
         self.phases = 1 if (self.world == 1 or exchange != "nccl") else max(1, int(exchange_phases or 1))
         self._peer_mem = exchange  # "p2p": consumers pull from the producer's buffer; "push": producers store into the consumer's
         # node -> GPU map: balanced min-cut by default (every rank computes the same map), "contiguous", or a list
@@ -122,29 +126,31 @@ class ADMMEngine:
         deg = [int(sp.nbr_ptr[g + 1] - sp.nbr_ptr[g]) for g in self.loc]
         self.q_uniform = 1.0
         self.Qdir = None
-        nnz_loc = sum(deg)
+        # directed pairs (i, j) whose Q_ij this rank needs: every local node's neighbours in G.neighbors order, then --
+        # single-owner exchange -- the peer's end of the cut edges this rank updates (for that end's penalty value)
+        dirs = [(g, int(sp.nbr_idx[k])) for g in self.loc for k in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1])]
+        if self._owner:
+            for le in sp.local_edges:
+                if le.peer >= 0 and le.owner == self.rank:
+                    dirs.append((le.gj, le.gi) if le.i_local else (le.gi, le.gj))
+        self.dirslot = {d: k for k, d in enumerate(dirs)}
         if Q is None or np.isscalar(Q):
             self.q_uniform = 1.0 if Q is None else float(Q)
         elif getattr(Q, "_admm_b200_spec", None) is not None:
             # block_3.make_precisions provider: upload the W vectors once, form Q_ij on the device
             mode, Wl = Q._admm_b200_spec
-            need = sorted({g for g in self.loc} | {int(sp.nbr_idx[k]) for g in self.loc
-                                                   for k in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1])})
+            need = sorted({g for d in dirs for g in d} | set(self.loc))
             wmap = {g: k for k, g in enumerate(need)}
             Wd = torch.from_numpy(np.stack([np.asarray(Wl[g], dtype=np.float32).reshape(-1) for g in need])).to(self.dev)
             self.h2d_bytes += Wd.numel() * 4
-            ii = torch.tensor([wmap[g] for g in self.loc for _ in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1])], device=self.dev)
-            jj = torch.tensor([wmap[int(sp.nbr_idx[k])] for g in self.loc
-                               for k in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1])], device=self.dev)
+            ii = torch.tensor([wmap[a] for a, _ in dirs] or [0], device=self.dev)
+            jj = torch.tensor([wmap[b] for _, b in dirs] or [0], device=self.dev)
             Wi_, Wj_ = Wd[ii], Wd[jj]
             qd = 0.5 * (Wi_ + Wj_) if mode == "arithmetic" else (Wi_ * Wj_) / (Wi_ + Wj_)
             self.Qdir = torch.clamp_min(qd, 1e-12).contiguous()
             del Wi_, Wj_, qd
         else:
-            qv = []
-            for g in self.loc:
-                for k in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1]):
-                    qv.append(np.asarray(Q(g, int(sp.nbr_idx[k])), dtype=np.float32).reshape(-1))
+            qv = [np.asarray(Q(a, b), dtype=np.float32).reshape(-1) for a, b in dirs]
             first = qv[0][0] if qv else 1.0
             if all(np.all(q == first) for q in qv):
                 self.q_uniform = float(first)
@@ -225,7 +231,11 @@ class ADMMEngine:
         self._host_thread = threading.Thread(target=_alloc, daemon=True)
         self._host_thread.start()
 
-        self._build_tables()
+        if self._owner and self.exchange_mode == "p2p":
+            self._build_tables_owner()
+        else:
+            self._owner = False
+            self._build_tables()
         self.st = nat.State()
         self._fill_state(fuse_pupdate)
         self.k = 0
@@ -250,7 +260,7 @@ class ADMMEngine:
         self._ipc_mine, self._ipc_opened = None, []
         # measured on B200s (profiles/README.md): the producer-side push on a side stream wins at every rank count once
         # the node map is the balanced min-cut one (2 GPUs: 22.6 vs 22.9 ms pull; 8 GPUs: 8.35 vs 9.0 NCCL, 9.2 pull)
-        self._push = exchange in ("push", "auto")
+        self._push = exchange in ("push", "auto", "owner")
         if exchange == "nccl":
             return "nccl"
         ok, handle = 1, b""
@@ -295,7 +305,7 @@ class ADMMEngine:
                 nat.check(L.admm_plan_set(self.plan.handle, nat.OPT_PACK_BLOCKS, nsm * per_sm), "admm_plan_set")
             return "p2p"
         self._release_ipc(sync=False)     # falling back to NCCL: give the IPC buffer and any mapped peers back now
-        if exchange in ("p2p", "push"):
+        if exchange in ("p2p", "push", "owner"):
             raise RuntimeError("peer-memory exchange requested but CUDA IPC setup failed on some rank")
         return "nccl"
 
@@ -329,12 +339,6 @@ class ADMMEngine:
                 qa.append(self._addr(self.Qdir, k) if self.Qdir is not None else 0)
                 k += 1
             ptr.append(len(za))
-        self.dirslot = {}
-        k = 0
-        for g in self.loc:
-            for kk in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1]):
-                self.dirslot[(g, int(sp.nbr_idx[kk]))] = k
-                k += 1
         i64 = lambda a: torch.tensor(a if len(a) else [0], dtype=torch.int64, device=self.dev)  # noqa: E731
         self.nbr_ptr = torch.tensor(ptr, dtype=torch.int32, device=self.dev)
         self.nbr_z, self.nbr_y, self.nbr_q = i64(za), i64(ya), i64(qa)
@@ -354,7 +358,7 @@ class ADMMEngine:
             Wj = self._addr(self.W, self.Wmap[le.gj]) if self.W is not None else 0
             qij = self._addr(self.Qdir, self.dirslot[(le.gi, le.gj)]) if (self.Qdir is not None and le.i_local) else 0
             qji = self._addr(self.Qdir, self.dirslot[(le.gj, le.gi)]) if (self.Qdir is not None and le.j_local) else 0
-            ed.append([xi, xj, yi, yj, self._addr(self.z, s), ai, aj, Wi, Wj, qij, qji])
+            ed.append([xi, xj, yi, yj, self._addr(self.z, s), ai, aj, Wi, Wj, qij, qji, 0, 0])
             gi.append(le.gi)
             gj.append(le.gj)
             fl.append((1 if le.i_local else 0) | (2 if le.j_local else 0) | (4 if le.owns_dual else 0))
@@ -367,7 +371,8 @@ class ADMMEngine:
         self.pack_rows = [sum(1 for t in packs if t[0] < k) for k in range(self.phases + 1)]
         pack_les = [t[2] for t in packs]
         packs = [t[1] for t in packs]
-        self.edge_desc = torch.tensor(ed if ed else [[0] * 11], dtype=torch.int64, device=self.dev)
+        self.edge_desc = torch.tensor(ed if ed else [[0] * 13], dtype=torch.int64, device=self.dev)
+        self.E_run = len(ordered)
         i32 = lambda a: torch.tensor(a if len(a) else [0], dtype=torch.int32, device=self.dev)  # noqa: E731
         self.edge_gi, self.edge_gj, self.edge_fl = i32(gi), i32(gj), i32(fl)
         epos_of = {le.e: k for k, le in enumerate(ordered)}       # global edge id -> position in the edge arrays
@@ -394,6 +399,73 @@ class ADMMEngine:
                 pk1[k, 2] = self._pack_out(le, 1)
             self.edge_desc_par = [self.edge_desc, ed1]
             self.pack_desc_par = [self.pack_desc, pk1]
+
+    def _build_tables_owner(self):
+        """Tables of the single-owner exchange.  This rank's edge pass covers its local edges and the cut edges it owns;
+        for an owned cut edge the peer's x arrives in this rank's buffer (slot of the edge) and v = z' - y' of the
+        peer's end is stored into the PEER's buffer by the edge kernel.  For a cut edge owned by the peer this rank only
+        sends x of its end and its rhs0 reads the returned v (as "z", with a zero "y")."""
+        torch, sp, n = self.torch, self.sp, self.n
+        mine = lambda le: le.peer < 0 or le.owner == self.rank      # noqa: E731
+        inbox = lambda e: self._ipc_mine + self._my_slot[e] * n * 4    # noqa: E731
+        peer_inbox = lambda le: self._peer_base[le.peer] + self._peer_slot[le.peer][le.e] * n * 4   # noqa: E731
+        self._zero = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        # K6 neighbour tables
+        ptr, za, ya, qa = [0], [], [], []
+        for g in self.loc:
+            for kk in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1]):
+                le = sp.local_edges[sp.eslot[int(sp.nbr_edge[kk])]]
+                if mine(le):
+                    za.append(self._addr(self.z, le.slot))
+                    ya.append(self._addr(self.y, le.slot, int(sp.nbr_end[kk])))
+                else:
+                    za.append(inbox(le.e))
+                    ya.append(self._zero.data_ptr())
+                qa.append(self._addr(self.Qdir, self.dirslot[(g, int(sp.nbr_idx[kk]))]) if self.Qdir is not None else 0)
+            ptr.append(len(za))
+        i64 = lambda a: torch.tensor(a if len(a) else [0], dtype=torch.int64, device=self.dev)  # noqa: E731
+        i32 = lambda a: torch.tensor(a if len(a) else [0], dtype=torch.int32, device=self.dev)  # noqa: E731
+        self.nbr_ptr = torch.tensor(ptr, dtype=torch.int32, device=self.dev)
+        self.nbr_z, self.nbr_y, self.nbr_q = i64(za), i64(ya), i64(qa)
+        # K5 descriptors: local edges first (they run under the push), then the owned cut edges
+        ordered = [le for le in sp.local_edges if le.peer < 0] + [le for le in sp.local_edges if le.peer >= 0 and mine(le)]
+        self.n_edges_local = sum(1 for le in sp.local_edges if le.peer < 0)
+        ed, gi, gj, fl = [], [], [], []
+        qaddr = lambda a, b: self._addr(self.Qdir, self.dirslot[(a, b)]) if self.Qdir is not None else 0   # noqa: E731
+        for le in ordered:
+            s = le.slot
+            xi = self._addr(self.x, sp.g2l[le.gi]) if le.i_local else inbox(le.e)
+            xj = self._addr(self.x, sp.g2l[le.gj]) if le.j_local else inbox(le.e)
+            Wi = self._addr(self.W, self.Wmap[le.gi]) if self.W is not None else 0
+            Wj = self._addr(self.W, self.Wmap[le.gj]) if self.W is not None else 0
+            vi = peer_inbox(le) if not le.i_local else 0
+            vj = peer_inbox(le) if not le.j_local else 0
+            ed.append([xi, xj, self._addr(self.y, s, 0), self._addr(self.y, s, 1), self._addr(self.z, s), 0, 0, Wi, Wj,
+                       qaddr(le.gi, le.gj), qaddr(le.gj, le.gi), vi, vj])
+            gi.append(le.gi)
+            gj.append(le.gj)
+            fl.append(1 | 2 | 4 | (8 if not le.i_local else 0) | (16 if not le.j_local else 0))
+        self.edge_desc = torch.tensor(ed if ed else [[0] * 13], dtype=torch.int64, device=self.dev)
+        self.E_run = len(ordered)
+        self.edge_gi, self.edge_gj, self.edge_fl = i32(gi), i32(gj), i32(fl)
+        epos_of = {le.e: k for k, le in enumerate(ordered)}
+        fptr, fepos, fend = [0], [], []
+        for g in self.loc:
+            for kk in range(sp.nbr_ptr[g], sp.nbr_ptr[g + 1]):
+                fepos.append(epos_of.get(int(sp.nbr_edge[kk]), -1))     # -1: the owning peer adds this node's pieces
+                fend.append(int(sp.nbr_end[kk]))
+            fptr.append(len(fepos))
+        self.fin_ptr, self.fin_epos, self.fin_end = i32(fptr), i32(fepos), i32(fend)
+        self.node_gid = i32(self.loc)
+        # push items: x of this rank's end of every cut edge the peer owns (y = 0: plain copy), peers served in rotation
+        sends = [le for le in sp.local_edges if le.peer >= 0 and not mine(le)]
+        sends.sort(key=lambda le: ((le.peer - self.rank) % self.world, le.e))
+        packs = [[self._addr(self.x, sp.g2l[le.gi if le.i_local else le.gj]), 0, peer_inbox(le)] for le in sends]
+        self.pack_rows = [0, len(packs)]
+        self.pack_desc = torch.tensor(packs if packs else [[0, 0, 0]], dtype=torch.int64, device=self.dev)
+        self.n_pack = len(packs)
+        self.edge_desc_par = [self.edge_desc, self.edge_desc]      # single-buffered: two barriers per iteration order it
+        self.pack_desc_par = [self.pack_desc, self.pack_desc]
 
     def _fill_state(self, fuse):
         st = self.st
@@ -508,8 +580,8 @@ class ADMMEngine:
         """K5 on the local edges (overlaps the exchange), then on the cut edges, then the residual row."""
         L, h = nat.lib(), self.plan.handle
         sref = ctypes.byref(self.st)
-        nl, E = self.n_edges_local, self.E
-        esz = 11 * 8
+        nl, E = self.n_edges_local, self.E_run
+        esz = 13 * 8
         par = self.k & 1 if self.exchange_mode == "p2p" else 0
         desc = self.edge_desc_par[par]
         if nl:
@@ -524,6 +596,8 @@ class ADMMEngine:
             # iteration instead of two (a dedicated one-float all-reduce only when no row is pending)
             if not self._flush_row():
                 self.dist.all_reduce(self._bar, group=self.group)
+            # (single-owner exchange: the row was reduced right after the edge pass -- that collective is the barrier
+            #  before anyone's next rhs0 reads the returned v -- so this is the dedicated one)
         for r in reqs:
             r.wait()          # stream-level wait: the compute stream now depends on the received buffers
         if getattr(self, "_edges_timed", None):
@@ -537,14 +611,14 @@ class ADMMEngine:
                                          self.sums.data_ptr() + nl * 5 * 8, self._stream()), "admm_edge_update")
         # history row k is written in place (device-side row index = the device's iteration counter)
         nat.check(L.admm_finalize(h, sref, self.sums.data_ptr(), self.edge_gi.data_ptr(), self.edge_gj.data_ptr(),
-                                  self.edge_fl.data_ptr(), self.E, self.n_edges_local, self.node_gid.data_ptr(),
+                                  self.edge_fl.data_ptr(), E, self.n_edges_local, self.node_gid.data_ptr(),
                                   self.fin_ptr.data_ptr(), self.fin_epos.data_ptr(), self.fin_end.data_ptr(), self.Vg,
                                   self.hist.data_ptr(), self._stream()), "admm_finalize")
         if self.world > 1:
             # the only data collective: the sum of the ranks' rows.  Peer-memory exchange: deferred to the
             # next iteration's barrier (or to whoever reads the residuals first); NCCL exchange: right away
             self._pending_row = self.k
-            if self.exchange_mode != "p2p":
+            if self.exchange_mode != "p2p" or self._owner:
                 self._flush_row()
 
     def _flush_row(self):

@@ -77,10 +77,12 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
     eps label of the accepted try (min(1e-2, eps_target) / 5^tries) and `history["tighten_history"]` the tries.
     `Qij_diag_fn` may be a callable (i, j) -> n-vector (block_3 provider), a scalar, or None (uniform 1).
     Under torch.distributed (NCCL) the nodes are sharded over the ranks; every rank returns the full result
-    (`distributed=False` keeps the whole graph on this rank's GPU).  `exchange`: "p2p" reads the cut-edge iterates
+    (`distributed=False` keeps the whole graph on this rank's GPU).  `exchange`: "owner" (= "auto") lets ONE rank update each cut edge: the other
+    rank stores x of its end into the owner's memory over NVLink and the owner's edge kernel stores v = z' - y' back;
+    "p2p" reads the cut-edge iterates
     straight from the peers' memory over NVLink inside the edge kernel (CUDA IPC), "push" stores them into the
     peers' memory from the pack kernel on a side stream, "nccl" uses grouped send/recv (optionally posted in
-    `exchange_phases` pieces as node blocks finish), "auto" = push.  `partition`: node -> GPU map, "auto" (balanced min-cut
+    `exchange_phases` pieces as node blocks finish).  `partition`: node -> GPU map, "auto" (balanced min-cut
     for V <= 256), "mincut", "contiguous" ((i*G)//V) or an explicit list of ranks.  `gather`: "all" (every rank returns every node's x, like the single-process
     reference) or "rank0" (only rank 0 receives the full list; the others get their own nodes and None elsewhere).
     """

@@ -425,7 +425,7 @@ rhs0_kernel(const RhsParams P) {
 // =================================================================================================
 struct EdgePtrs {
     const float *xi, *xj, *ai_r, *aj_r, *Wi, *Wj, *qij, *qji;
-    float *yi, *yj, *z;
+    float *yi, *yj, *z, *vi, *vj;
     float q_uniform;
 };
 
@@ -462,6 +462,7 @@ edge_kernel(const EdgeParams P) {
     e.ai_r = reinterpret_cast<const float*>(d.ai); e.aj_r = reinterpret_cast<const float*>(d.aj);
     e.Wi = reinterpret_cast<const float*>(d.Wi); e.Wj = reinterpret_cast<const float*>(d.Wj);
     e.qij = reinterpret_cast<const float*>(d.qij); e.qji = reinterpret_cast<const float*>(d.qji);
+    e.vi = reinterpret_cast<float*>(d.vi); e.vj = reinterpret_cast<float*>(d.vj);
     e.q_uniform = P.q_uniform;
     float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -483,6 +484,9 @@ edge_kernel(const EdgeParams P) {
         st4(e.z + o, zn);
         if (e.xi) st4(e.yi + o, yin);
         if (e.xj) st4(e.yj + o, yjn);
+        // single-owner exchange: v = z' - y' of a peer's node goes straight into the peer's memory (posted NVLink stores)
+        if (e.vi) st4(e.vi + o, make_float4(zn.x - yin.x, zn.y - yin.y, zn.z - yin.z, zn.w - yin.w));
+        if (e.vj) st4(e.vj + o, make_float4(zn.x - yjn.x, zn.y - yjn.y, zn.z - yjn.z, zn.w - yjn.w));
     }
     for (long long k = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += (long long)gridDim.x * blockDim.x) {
         float zn, yin = 0.f, yjn = 0.f;
@@ -492,6 +496,8 @@ edge_kernel(const EdgeParams P) {
         e.z[k] = zn;
         if (e.xi) e.yi[k] = yin;
         if (e.xj) e.yj[k] = yjn;
+        if (e.vi) e.vi[k] = zn - yin;
+        if (e.vj) e.vj[k] = zn - yjn;
     }
     block_sum<5>(s, red);
     grid_reduce_store<5>(s, P.part + (long long)blockIdx.y * gridDim.x * 5, P.counter + blockIdx.y, blockIdx.x,
@@ -510,6 +516,12 @@ pack_kernel(const PackParams P) {
         float* __restrict__ o = reinterpret_cast<float*>(d.out);
         const long long n4 = ((P.n & 3) == 0) ? (P.n >> 2) : 0;
         const long long step = (long long)gridDim.x * blockDim.x;
+        if (!y) {   // single-owner exchange: the peer that updates the edge gets x itself
+#pragma unroll 4
+            for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += step) st4(o + 4 * k, ld4(x + 4 * k));
+            for (long long k = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += step) o[k] = x[k];
+            continue;
+        }
 #pragma unroll 4
         for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += step) {
             const float4 a = ld4(x + 4 * k), b = ld4(y + 4 * k);
@@ -540,6 +552,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams P) {
         double a = 0.0, b = 0.0, d = 0.0;
         for (int k = P.nbr_ptr[v]; k < P.nbr_ptr[v + 1]; ++k) {
             const int e = P.nbr_epos[k], end = P.nbr_end[k];
+            if (e < 0) continue;      // updated by the peer that owns the edge: it adds this node's pieces to its row
             const double* s = P.sums + (long long)e * 5;
             a += s[end];
             b += s[3 + end];
@@ -573,7 +586,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams P) {
         // dual residual of owned cut edges also belongs to the REMOTE end's node (block_6_ver2:251-253)
         for (int e = P.E_local; e < P.E; ++e) {
             const int fl = P.edge_flags[e];
-            if ((fl & 4) && !(fl & 2)) dual[P.edge_gj[e]] += rho2 * P.sums[(long long)e * 5 + 2];
+            const double* s = P.sums + (long long)e * 5;
+            if (fl & 24) {            // single-owner exchange: every per-node piece of the remote end
+                const int g = (fl & 8) ? P.edge_gi[e] : P.edge_gj[e], end = (fl & 8) ? 0 : 1;
+                pri[g] += s[end]; pen[g] += s[3 + end]; dual[g] += rho2 * s[2];
+            } else if ((fl & 4) && !(fl & 2)) dual[P.edge_gj[e]] += rho2 * s[2];
         }
     }
     if (P.iter_dev) {      // every thread has read the counter (row pointer) before the barrier above

@@ -74,6 +74,8 @@ struct EdgeDesc {
     unsigned long long ai, aj;   // received a = x + y of a remote end
     unsigned long long Wi, Wj;   // per-pixel precisions for the W-weighted fusion (0: midpoint)
     unsigned long long qij, qji; // Q vectors for the penalty value (0: uniform)
+    unsigned long long vi, vj;   // single-owner exchange: where to store v = z' - y' of an end whose node lives on a peer
+                                 //   (that node's next rhs0 needs exactly q .* v); 0: nothing to store
 };
 
 struct EdgeParams {
@@ -90,7 +92,9 @@ struct FinalizeParams {
     const double* sums;       // [E][5]
     const int* edge_gi;       // [E] global node ids
     const int* edge_gj;
-    const int* edge_flags;    // bit0: i local, bit1: j local, bit2: owns the dual residual
+    const int* edge_flags;    // bit0: count end i in r2, bit1: end j, bit2: owns the dual residual, bit3 / bit4: end i / j
+                              //   belongs to a node of another rank and THIS rank updates the edge (single-owner exchange):
+                              //   its per-node pieces are added to the row here
     const double* scal;       // [V][NSCAL]
     const int* node_gid;      // [V]
     const int* nbr_ptr;       // [V+1] incident-edge lists of the local nodes (G.neighbors order)

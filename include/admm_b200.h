@@ -101,6 +101,8 @@ typedef struct admm_node_ctl { int active, tries, wpar, pad; } admm_node_ctl;
 /* One undirected edge (i<j) as seen by this rank; addresses are device pointers as integers. */
 typedef struct admm_edge {
     unsigned long long xi, xj, yi, yj, z, ai, aj, Wi, Wj, qij, qji;
+    unsigned long long vi, vj; /* single-owner exchange: where v = z' - y' of an end whose node lives on a peer is stored
+                                  (the peer's mapped buffer; its next rhs0 reads it as "z" with "y" = 0), or 0 */
 } admm_edge;
 
 typedef struct admm_pack_item { unsigned long long x, y, out; } admm_pack_item;
@@ -183,11 +185,13 @@ int admm_accept(admm_plan* plan, admm_state* st, int node0, int nodes, double ep
  * d_sums[E][5] = |x_i-z'|^2, |x_j-z'|^2, |z'-z|^2, pen_i, pen_j per edge. */
 int admm_edge_update(admm_plan* plan, const admm_state* st, const admm_edge* d_edges, int nedges,
                      double* d_sums, void* stream);
+/* out = x + y per item; y == 0: out = x (single-owner exchange: the peer that updates the edge gets x itself) */
 int admm_pack(admm_plan* plan, const admm_pack_item* d_items, int nitems, void* stream);
 /* history row [r2, s2, pri_node[Vg], dual_node[Vg], pen[Vg], mse[Vg], tv[Vg], gn2[Vg], img[Vg], tries[Vg]] (doubles;
  * tries = extra solves the a14 rule spent on the node, 0 without a control table).
  * Edge arrays list the rank's local edges first (nedges_local), then its cut edges; flags: bit0 i local, bit1 j
- * local, bit2 this rank owns the edge's dual residual.  nbr_* = incident-edge CSR of the local nodes
+ * local, bit2 this rank owns the edge's dual residual, bit3 / bit4 end i / j belongs to a peer's node whose edge THIS rank
+ * updates (its per-node pieces are added to the row here).  nbr_* = incident-edge CSR of the local nodes
  * (G.neighbors order): position of the edge in the edge arrays and which end the node is. */
 int admm_finalize(admm_plan* plan, const admm_state* st, const double* d_sums, const int* d_edge_gi,
                   const int* d_edge_gj, const int* d_edge_flags, int nedges, int nedges_local,

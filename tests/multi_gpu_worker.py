@@ -45,6 +45,13 @@ def main():
         xc, hc = decentralized_admm(ops, sinos, G, Wl, Q, N, partition="contiguous", **kw)   # default map: balanced min-cut
         assert all(np.array_equal(a, b) for a, b in zip(xs, xc))          # the map moves nodes, not arithmetic
         assert np.allclose(hs["primal"], hc["primal"], rtol=1e-10)          # (the all-reduce sums ranks' shares in another order)
+        # single-owner exchange (the default): one rank updates a cut edge and returns v = z' - y' -- the same fp32
+        # operations on the same operands, so x is bit-identical; the per-node fp64 sums are added in another order
+        xw, hw = decentralized_admm(ops, sinos, G, Wl, Q, N, exchange="owner", **kw)
+        assert all(np.array_equal(a, b) for a, b in zip(xs, xw))
+        for key in ("primal", "dual", "pri_per_node", "dual_per_node", "obj_per_node", "mse_sino_per_node"):
+            assert np.allclose(np.array(hs[key]), np.array(hw[key]), rtol=1e-10, atol=1e-300), key
+        assert np.array_equal(np.array(hs["tighten_history"]), np.array(hw["tighten_history"]))
         assert all(np.array_equal(a, b) for a, b in zip(xs, xp)) and hs["primal"] == hp["primal"]
         assert all(np.array_equal(a, b) for a, b in zip(xs, x2)) and hs["primal"] == h2["primal"]
         x1, h1 = decentralized_admm(ops, sinos, G, Wl, Q, N, distributed=False, **kw)

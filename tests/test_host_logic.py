@@ -122,7 +122,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert set(nat.EXPORTS) <= declared
     assert L.admm_version() == 200
     assert ctypes.sizeof(nat.State) == L.admm_abi_sizeof(0) == 272
-    assert L.admm_abi_sizeof(1) == 11 * 8 and L.admm_abi_sizeof(2) == 3 * 8 and L.admm_abi_sizeof(3) == 16
+    assert L.admm_abi_sizeof(1) == 13 * 8 and L.admm_abi_sizeof(2) == 3 * 8 and L.admm_abi_sizeof(3) == 16
 
 
 def test_no_cpu_fallback_without_device():
