@@ -103,6 +103,7 @@ def lib():
     L.admm_accept.argtypes = [vp, ctypes.POINTER(State), i, i, d, i, i, vp]
     L.admm_edge_update.argtypes = [vp, ctypes.POINTER(State), vp, i, vp, vp]
     L.admm_pack.argtypes = [vp, vp, i, vp]
+    L.admm_push_copy.argtypes = [vp, vp, i, vp]
     L.admm_finalize.argtypes = [vp, ctypes.POINTER(State), vp, vp, vp, vp, i, i, vp, vp, vp, vp, i, vp, vp]
     L.admm_grad2d_host.argtypes = [i, vp, vp, vp]
     L.admm_div2d_host.argtypes = [i, vp, vp, i, vp]
@@ -114,7 +115,7 @@ def lib():
     L.admm_profile_enable.argtypes = [i]
     L.admm_profile_read.argtypes = [vp, vp]
     for name in ("admm_ipc_alloc", "admm_ipc_open", "admm_ipc_close", "admm_ipc_free", "admm_grad2d_host", "admm_div2d_host", "admm_kt_subgrad_host", "admm_profile_enable", "admm_profile_read", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host", "admm_adjoint_host",
-                 "admm_rhs0", "admm_x_update", "admm_tv_pass", "admm_accept", "admm_edge_update", "admm_pack", "admm_finalize"):
+                 "admm_rhs0", "admm_x_update", "admm_tv_pass", "admm_accept", "admm_edge_update", "admm_pack", "admm_push_copy", "admm_finalize"):
         getattr(L, name).restype = i
     if L.admm_abi_sizeof(0) != ctypes.sizeof(State):
         raise RuntimeError(f"libadmm_b200.so admm_state is {L.admm_abi_sizeof(0)} bytes, the binding's mirror "
@@ -126,7 +127,7 @@ def lib():
 EXPORTS = ("admm_version", "admm_abi_sizeof", "admm_last_error", "admm_device_count", "admm_plan_create",
            "admm_plan_create_dense", "admm_plan_upload_dense", "admm_plan_destroy",
            "admm_plan_info", "admm_plan_set", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host",
-           "admm_adjoint_host", "admm_colnorm2_host", "admm_rhs0", "admm_x_update", "admm_edge_update", "admm_pack", "admm_finalize",
+           "admm_adjoint_host", "admm_colnorm2_host", "admm_rhs0", "admm_x_update", "admm_edge_update", "admm_pack", "admm_push_copy", "admm_finalize",
            "admm_tv_pass", "admm_accept", "admm_launch_count", "admm_profile_enable", "admm_profile_read", "admm_grad2d_host",
            "admm_div2d_host", "admm_kt_subgrad_host", "admm_ipc_alloc", "admm_ipc_open", "admm_ipc_close", "admm_ipc_free")
 

@@ -462,6 +462,10 @@ class ADMMEngine:
         sends.sort(key=lambda le: ((le.peer - self.rank) % self.world, le.e))
         packs = [[self._addr(self.x, sp.g2l[le.gi if le.i_local else le.gj]), 0, peer_inbox(le)] for le in sends]
         self.pack_rows = [0, len(packs)]
+        # host copy of the items for the copy-engine push (ADMM_B200_PUSH_CE=1): plain copies need no kernel
+        import os
+        self._push_ce = os.environ.get("ADMM_B200_PUSH_CE", "0") == "1"
+        self._pack_host = np.ascontiguousarray(np.array(packs if packs else [[0, 0, 0]], dtype=np.uint64))
         self.pack_desc = torch.tensor(packs if packs else [[0, 0, 0]], dtype=torch.int64, device=self.dev)
         self.n_pack = len(packs)
         self.edge_desc_par = [self.edge_desc, self.edge_desc]      # single-buffered: two barriers per iteration order it
@@ -563,7 +567,10 @@ class ADMMEngine:
             torch = self.torch
             main = torch.cuda.current_stream()
             self._side.wait_stream(main)          # x is final
-            if k1 > k0:
+            if k1 > k0 and self._owner and getattr(self, "_push_ce", False):
+                nat.check(nat.lib().admm_push_copy(self.plan.handle, self._pack_host.ctypes.data + k0 * 24, k1 - k0,
+                                                   ctypes.c_void_p(self._side.cuda_stream)), "admm_push_copy")
+            elif k1 > k0:
                 nat.check(nat.lib().admm_pack(self.plan.handle, self.pack_desc_par[par].data_ptr() + k0 * 24, k1 - k0,
                                               ctypes.c_void_p(self._side.cuda_stream)), "admm_pack")
             self._pushed = torch.cuda.Event()

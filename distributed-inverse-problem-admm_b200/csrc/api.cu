@@ -618,6 +618,19 @@ extern "C" int admm_pack(admm_plan* p, const admm_pack_item* d_items, int nitems
     return ADMM_OK;
 }
 
+// Copy-engine form of the x push of the single-owner exchange: one cudaMemcpyAsync per item (x -> out, n floats) on the
+// given stream; `h_items` is a HOST array.  No SM is used, so the transfer does not compete with the TV / edge kernels.
+extern "C" int admm_push_copy(admm_plan* p, const admm_pack_item* h_items, int nitems, void* stream) {
+    if (!p || (nitems > 0 && !h_items)) return fail(ADMM_ERR_ARG, "admm_push_copy: null argument");
+    const size_t bytes = (size_t)p->N * p->N * sizeof(float);
+    for (int k = 0; k < nitems; ++k) {
+        if (h_items[k].y != 0) return fail(ADMM_ERR_ARG, "admm_push_copy: item is not a plain copy (y != 0)");
+        CK(cudaMemcpyAsync(reinterpret_cast<void*>(h_items[k].out), reinterpret_cast<const void*>(h_items[k].x), bytes,
+                           cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+    return ADMM_OK;
+}
+
 extern "C" int admm_finalize(admm_plan* p, const admm_state* s, const double* d_sums, const int* d_edge_gi,
                              const int* d_edge_gj, const int* d_edge_flags, int nedges, int nedges_local,
                              const int* d_node_gid, const int* d_nbr_ptr, const int* d_nbr_epos, const int* d_nbr_end,

@@ -187,6 +187,8 @@ int admm_edge_update(admm_plan* plan, const admm_state* st, const admm_edge* d_e
                      double* d_sums, void* stream);
 /* out = x + y per item; y == 0: out = x (single-owner exchange: the peer that updates the edge gets x itself) */
 int admm_pack(admm_plan* plan, const admm_pack_item* d_items, int nitems, void* stream);
+/* the same plain copies (y == 0 items) through the copy engines: one cudaMemcpyAsync per item, `h_items` on the HOST */
+int admm_push_copy(admm_plan* plan, const admm_pack_item* h_items, int nitems, void* stream);
 /* history row [r2, s2, pri_node[Vg], dual_node[Vg], pen[Vg], mse[Vg], tv[Vg], gn2[Vg], img[Vg], tries[Vg]] (doubles;
  * tries = extra solves the a14 rule spent on the node, 0 without a control table).
  * Edge arrays list the rank's local edges first (nedges_local), then its cut edges; flags: bit0 i local, bit1 j
