@@ -14,7 +14,7 @@ _ROOT = os.path.dirname(_PKG)                      # distributed-inverse-problem
 CSRC = os.path.join(_ROOT, "csrc")
 LIB_PATH = os.path.join(_ROOT, "libadmm_b200.so")
 HEADER = os.path.join(os.path.dirname(_ROOT), "include", "admm_b200.h")
-SOURCES = ["api.cu", "projector.cu", "solver_kernels.cu", "tv_helpers.cu", "dense.cu"]
+SOURCES = ["api.cu", "projector.cu", "solver_kernels.cu", "tv_helpers.cu", "dense.cu", "rotsum.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -132,6 +132,7 @@ EXPORTS = ("admm_version", "admm_abi_sizeof", "admm_last_error", "admm_device_co
            "admm_div2d_host", "admm_kt_subgrad_host", "admm_ipc_alloc", "admm_ipc_open", "admm_ipc_close", "admm_ipc_free")
 
 OPT_PACK_BLOCKS = 0
+OPT_IMPL = 1
 
 KC_NAMES = ("fwd", "fwd_reduce", "back_plain", "back_hp", "back_resid0", "colnorm2", "tv", "cg_update", "p_update",
             "sino_axpy", "sino_resid", "rhs0", "edge", "pack", "finalize", "fwd_fused", "accept")

@@ -21,11 +21,22 @@ def _torch():
     return torch
 
 
+def _impl_name(impl):
+    """ODL backend names -> the two discretisations this build has: "joseph" (= ASTRA `linear`, ODL's default 2-D
+    parallel-beam backend when ASTRA is present) and "skimage" (rotate-and-sum bilinear)."""
+    if impl in ("joseph", "astra_cuda", "astra_cpu", None):
+        return "joseph"
+    if impl == "skimage":
+        return "skimage"
+    raise ValueError(f"unknown impl {impl!r}")
+
+
 class Plan:
     """Geometry + projector workspace of the nodes resident on one GPU (wraps `admm_plan`)."""
 
-    def __init__(self, N, thetas, D=None, det_w=2.0, device=0):
+    def __init__(self, N, thetas, D=None, det_w=2.0, device=0, impl="joseph"):
         nat.require_cuda()
+        self.impl = _impl_name(impl)
         self.N = int(N)
         self.D = int(D if D is not None else N)
         self.det_w = float(det_w)
@@ -45,6 +56,8 @@ class Plan:
             raise RuntimeError("admm_plan_create failed: " + L.admm_last_error().decode())
         self.handle = ctypes.c_void_p(h)
         self.n = self.N * self.N
+        if self.impl == "skimage":
+            nat.check(L.admm_plan_set(self.handle, nat.OPT_IMPL, 1), "admm_plan_set")
         self.part_floats = int(L.admm_plan_info(self.handle, nat.INFO_PART_FLOATS))
 
     def info(self, what):
@@ -111,7 +124,7 @@ class DensePlan(Plan):
         self.part_floats = int(L.admm_plan_info(self.handle, nat.INFO_PART_FLOATS))
 
 
-def make_plan(N, ops, D=None, det_w=2.0, device=0):
+def make_plan(N, ops, D=None, det_w=2.0, device=0, impl="joseph"):
     """One plan over the operators of the nodes resident on a GPU: matrix-free (`RayTransformCUDA`: angle arrays) or
     dense (`DenseOperatorCUDA` / 2-D ndarrays)."""
     dense = [isinstance(o, DenseOperatorCUDA) or (isinstance(o, np.ndarray) and o.ndim == 2) for o in ops]
@@ -119,7 +132,11 @@ def make_plan(N, ops, D=None, det_w=2.0, device=0):
         return DensePlan(N, [o.matrix if isinstance(o, DenseOperatorCUDA) else o for o in ops], device)
     if any(dense):
         raise TypeError("mixing dense matrices and matrix-free operators in one A_dense_list is not supported")
-    return Plan(N, [np.asarray(o.angles if hasattr(o, "angles") else o, dtype=np.float64) for o in ops], D, det_w, device)
+    impls = {getattr(o, "impl", impl) for o in ops}
+    if len(impls) > 1:
+        raise TypeError("all node operators must use the same projector discretisation (impl)")
+    return Plan(N, [np.asarray(o.angles if hasattr(o, "angles") else o, dtype=np.float64) for o in ops], D, det_w, device,
+                impl=impls.pop())
 
 
 class DenseOperatorCUDA:
@@ -301,8 +318,7 @@ class RayTransformCUDA:
     """
 
     def __init__(self, N, theta, D=None, det_w=2.0, device=0, impl="joseph", angle_cell=None):
-        if impl not in ("joseph", "astra_cuda", "astra_cpu", "skimage", None):
-            raise ValueError(f"unknown impl {impl!r}")
+        self.impl = _impl_name(impl)     # "skimage": the rotate-and-sum variant (csrc/rotsum.cu), otherwise Joseph
         self.N = int(N)
         self.D = int(D if D is not None else N)
         self.det_w = float(det_w)
@@ -326,7 +342,7 @@ class RayTransformCUDA:
 
     def plan(self):
         if self._plan is None:
-            self._plan = Plan(self.N, [self.theta], self.D, self.det_w, self.device)
+            self._plan = Plan(self.N, [self.theta], self.D, self.det_w, self.device, impl=self.impl)
         return self._plan
 
     def _forward_np(self, x):
@@ -375,4 +391,4 @@ def stack_operators(ops):
     """Aggregate operator = vstack of node operators (block_2_load_odl_data.py:58-63 intent)."""
     N, D, det_w = ops[0].N, ops[0].D, ops[0].det_w
     theta = np.concatenate([o.theta for o in ops])
-    return RayTransformCUDA(N, theta, D, det_w, ops[0].device, angle_cell=ops[0].range.cell_sides[0])
+    return RayTransformCUDA(N, theta, D, det_w, ops[0].device, impl=ops[0].impl, angle_cell=ops[0].range.cell_sides[0])

@@ -46,7 +46,7 @@ class ADMMEngine:
                  node_prec=None, tv_mu=None, tv_sweeps=1, cg_iters=2, phantom_true=None, weighted_z=False,
                  device=0, dist=None, rank=0, world=1, group=None, node_group=None, fuse_pupdate=True,
                  max_iters=200, ax_refresh_every=10, exchange="auto", exchange_phases=None, partition="auto",
-                 acceptance=False, max_tighten=2, carry_residual=False, cuda_graph="auto"):
+                 acceptance=False, max_tighten=2, carry_residual=False, cuda_graph="auto", impl="joseph"):
         torch = _torch()
         nat.require_cuda()
         self.torch = torch
@@ -98,10 +98,12 @@ class ADMMEngine:
             raise ValueError("rank owns no node (more ranks than nodes)")
         n = self.n
         f32 = dict(dtype=torch.float32, device=self.dev)
-        self.plan = make_plan(N, [thetas[g] for g in self.loc], self.D, det_w, device)
+        self.plan = make_plan(N, [thetas[g] for g in self.loc], self.D, det_w, device, impl=impl)
         self.dense = bool(getattr(self.plan, "thetas", None) is None)
         if self.dense:      # explicit matrices: "sinograms" are plain vectors, and the fused CG staging does not apply
             self.D, fuse_pupdate = 1, 0
+        elif self.plan.impl != "joseph":    # rotate-and-sum variant: plain kernels, no fused CG staging
+            fuse_pupdate = 0
         A = self.A = self.plan.A
         self.node_group = int(node_group) if node_group else V
         self.ax_refresh_every = max(1, int(ax_refresh_every))
@@ -848,6 +850,7 @@ class NodeProblem:
         self.rho, self.lam = float(rho), float(lam_tv)
         self.mu = float(tv_mu) if tv_mu is not None else (self.rho if self.rho > 0 else 1.0)
         self.plan = make_plan(N, [op], op.D, op.det_w, device)
+        plain = isinstance(op, DenseOperatorCUDA) or getattr(self.plan, "impl", "joseph") != "joseph"
         n, f32 = self.n, dict(dtype=torch.float32, device=self.dev)
         up = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))).to(self.dev)  # noqa: E731
         self.b = up(b).reshape(self.plan.A, self.D)
@@ -878,7 +881,7 @@ class NodeProblem:
             setattr(st, name, getattr(self, name).data_ptr())
         st.xtrue = None
         st.stride, st.rho, st.lam, st.mu, st.q_uniform = n, self.rho, self.lam, self.mu, 1.0
-        st.w_parity, st.fuse_pupdate = 0, (0 if isinstance(op, DenseOperatorCUDA) else 2)
+        st.w_parity, st.fuse_pupdate = 0, (0 if plain else 2)
         ptr = torch.tensor([0, deg], dtype=torch.int32, device=self.dev)
         a = lambda t, k: t.data_ptr() + k * n * 4  # noqa: E731
         i64 = lambda v: torch.tensor(v if v else [0], dtype=torch.int64, device=self.dev)  # noqa: E731

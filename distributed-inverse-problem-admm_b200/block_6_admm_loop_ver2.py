@@ -26,7 +26,7 @@ def _node_geometry(A_list, N):
     for literal ndarray entries (the reference's own `A_dense_list`, block_2_load_odl_data.py:68-96: uploaded, no
     projector kernel, tiny problems only) -- and the common (N, D, det_w)."""
     from admm_b200 import DenseOperatorCUDA
-    ops, geo, dense = [], None, 0
+    ops, geo, dense, impls = [], None, 0, set()
     for A in A_list:
         if isinstance(A, np.ndarray) and A.ndim == 2:
             A = DenseOperatorCUDA(A, N)
@@ -37,6 +37,7 @@ def _node_geometry(A_list, N):
         elif hasattr(A, "angles"):
             g = (A.N, A.D, A.det_w)
             ops.append(np.asarray(A.angles, dtype=np.float64))
+            impls.add(getattr(A, "impl", "joseph"))
         else:
             raise TypeError("A_dense_list entries must be RayTransformCUDA operators (block_2_load_odl_data."
                             "load_odl_data builds them) or dense (m_i, N*N) matrices")
@@ -49,7 +50,9 @@ def _node_geometry(A_list, N):
         mb = sum(int(np.prod(o.shape)) for o in ops if hasattr(o, "matrix")) * 4 / 2 ** 20
         warnings.warn(f"decentralized_admm: {dense} dense operator(s) ({mb:.0f} MiB) are uploaded as they are and applied with "
                       f"plain dense matvec kernels; the matrix-free RayTransformCUDA operators are the fast path")
-    return ops, geo
+    if len(impls) > 1:
+        raise ValueError("all node operators must use the same projector discretisation (impl)")
+    return ops, geo, (impls.pop() if impls else "joseph")
 
 
 def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
@@ -95,7 +98,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
         raise ValueError("G is None: build_pixel_connected_Q_provider returns a graph only with plot_union=True "
                          "in the reference (SURVEY App. B-8); this build always returns one")
     num_nodes = len(A_dense_list)
-    thetas, (Ng, D, det_w) = _node_geometry(A_dense_list, N)
+    thetas, (Ng, D, det_w), impl = _node_geometry(A_dense_list, N)
     if Ng != N:
         raise ValueError(f"N={N} does not match the operators' image size {Ng}")
     n = N * N
@@ -122,7 +125,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                      weighted_z=weighted_z, device=device, dist=dist if world > 1 else None, rank=rank, world=world,
                      group=group, node_group=node_group, fuse_pupdate=fuse_pupdate, max_iters=max_iters,
                      ax_refresh_every=ax_refresh_every, exchange=exchange, exchange_phases=exchange_phases, partition=partition,
-                     acceptance=acceptance, max_tighten=max_tighten, carry_residual=carry_residual)
+                     acceptance=acceptance, max_tighten=max_tighten, carry_residual=carry_residual, impl=impl)
     eng._node_prec_all = node_prec
 
     def _solve_and_collect():

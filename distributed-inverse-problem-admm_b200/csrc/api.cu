@@ -95,6 +95,9 @@ struct admm_plan {
     // dense-matrix plans (admm_plan_create_dense): A = total matrix rows, D = 1, d_dense = [A][N*N] row-major
     bool dense = false;
     float* d_dense = nullptr;
+    // projector discretisation: 0 Joseph (the hot path), 1 rotate-and-sum bilinear ("skimage-flavoured", (f)-2)
+    int impl = 0;
+    float2* d_cs = nullptr;          // [A] fp32 (cos, sin) per angle row
 };
 
 static int check_nodes(const admm_plan* p, int node0, int nodes);
@@ -102,10 +105,12 @@ static int check_nodes(const admm_plan* p, int node0, int nodes);
 // the operator pair of a plan: strip projector / tile back-projector, or the dense matvecs
 static cudaError_t plan_forward(const admm_plan* p, const FwdParams& F, int nodes, const FwdReduceParams& R, cudaStream_t st) {
     if (p->dense) return launch_dense_forward(p->d_dense, p->d_anode, F, nodes, R, st);
+    if (p->impl == 1) return launch_rs_forward(p->d_cs, p->d_anode, p->det_w, F, nodes, R, st);
     return launch_forward(F, nodes, p->max_chunks, R, st);
 }
 static cudaError_t plan_back(const admm_plan* p, int mode, const BackParams& B, int nodes, cudaStream_t st) {
     if (p->dense) return launch_dense_back(p->d_dense, mode, B, nodes, st);
+    if (p->impl == 1) return launch_rs_back(p->d_cs, p->det_w, mode, B, nodes, st);
     return launch_back(mode, B, nodes, st);
 }
 
@@ -224,7 +229,11 @@ extern "C" admm_plan* admm_plan_create(int N, int D, double det_w, int V, const 
     ok &= cudaMalloc(&p->d_anode, sizeof(int) * anode.size()) == cudaSuccess;
     ok &= cudaMalloc(&p->d_recs, rec_bytes) == cudaSuccess;
     ok &= cudaMalloc(&p->d_jstart, js_bytes) == cudaSuccess;
+    ok &= cudaMalloc(&p->d_cs, sizeof(float2) * std::max(A, 1)) == cudaSuccess;
     if (ok) {
+        std::vector<float2> csh(std::max(A, 1));
+        for (int a = 0; a < A; ++a) csh[a] = make_float2(cos32[a], sin32[a]);
+        ok &= cudaMemcpy(p->d_cs, csh.data(), sizeof(float2) * std::max(A, 1), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(p->d_ang, p->recs_h.data(), sizeof(AngleRec) * std::max(A, 1), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(p->d_optr, optr.data(), sizeof(int) * optr.size(), cudaMemcpyHostToDevice) == cudaSuccess;
         ok &= cudaMemcpy(p->d_oidx, oidx.data(), sizeof(int) * oidx.size(), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -294,6 +303,7 @@ extern "C" void admm_plan_destroy(admm_plan* p) {
     if (!p) return;
     cudaFree(p->d_ang); cudaFree(p->d_optr); cudaFree(p->d_oidx); cudaFree(p->d_aptr); cudaFree(p->d_anode);
     cudaFree(p->d_recs); cudaFree(p->d_jstart); cudaFree(p->d_himg); cudaFree(p->d_hsino); cudaFree(p->d_dense);
+    cudaFree(p->d_cs);
     delete p;
 }
 
@@ -303,6 +313,10 @@ extern "C" int admm_plan_set(admm_plan* p, int what, long long value) {
         case ADMM_OPT_PACK_BLOCKS:
             if (value < 0 || value > 65535) return fail(ADMM_ERR_ARG, "admm_plan_set: pack blocks out of range");
             p->pack_blocks = (int)value;
+            return ADMM_OK;
+        case ADMM_OPT_IMPL:
+            if (p->dense || (value != 0 && value != 1)) return fail(ADMM_ERR_ARG, "admm_plan_set: bad projector variant");
+            p->impl = (int)value;
             return ADMM_OK;
         default: return fail(ADMM_ERR_ARG, "admm_plan_set: unknown option");
     }
@@ -318,7 +332,7 @@ extern "C" long long admm_plan_info(const admm_plan* p, int what) {
         case ADMM_INFO_PART_FLOATS: {
             const long long tiles = (long long)((p->N + 31) / 32) * ((p->N + 31) / 32);       // back-projector grid
             const long long tvblk = (long long)((p->N + 127) / 128) * ((p->N + 7) / 8);       // TV grid
-            const long long dblk = p->dense ? 3 * (((long long)p->N * p->N + 255) / 256) : 0;   // dense back-projector grid
+            const long long dblk = (p->dense || p->impl != 0) ? 3 * (((long long)p->N * p->N + 255) / 256) : 0;   // per-pixel back-projector grids
             return std::max(std::max(std::max(3 * tiles, 4 * tvblk), 5LL * 4096), dblk);
         }
         case ADMM_INFO_FWD_SPAN: return p->span;
@@ -484,8 +498,8 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
                              void* stream) {
     if (int e = check_nodes(p, node0, nodes)) return e;
     if (!s || sweeps < 1 || cg_iters < 0) return fail(ADMM_ERR_ARG, "admm_x_update: bad argument");
-    if (p->dense && s->fuse_pupdate != 0)
-        return fail(ADMM_ERR_ARG, "admm_x_update: dense-matrix plans need fuse_pupdate = 0 (the fused CG staging lives in the strip projector)");
+    if ((p->dense || p->impl != 0) && s->fuse_pupdate != 0)
+        return fail(ADMM_ERR_ARG, "admm_x_update: dense-matrix and rotate-and-sum plans need fuse_pupdate = 0 (the fused CG staging lives in the strip projector)");
     cudaStream_t st = (cudaStream_t)stream;
     const long long n = (long long)p->N * p->N, off = (long long)node0 * s->stride;
     const long long part_per = admm_plan_info(p, ADMM_INFO_PART_FLOATS);

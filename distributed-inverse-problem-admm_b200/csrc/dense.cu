@@ -5,7 +5,7 @@
 // trivially correct matvec kernels behind the same launch_forward / launch_back contract as the matrix-free
 // projector pair (same parameter blocks, same epilogue semantics, same deterministic reductions), so the solver
 // above them does not change.  Not a performance path: a dense A_i is 4 m_i n bytes (377 MB per node at cfg 1).
-#include "solver_kernels.cuh"
+#include "epilogue.cuh"
 
 namespace admm {
 
@@ -34,8 +34,7 @@ dense_back_kernel(const float* __restrict__ A, const BackParams P) {
     __shared__ __align__(16) float red[96];
     const int node = P.node0 + blockIdx.y;
     if (P.ctl && !P.ctl[node].active) return;
-    const int N = P.N;
-    const long long n = (long long)N * N;
+    const long long n = (long long)P.N * P.N;
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nb = (long long)blockIdx.y * P.stride;
     const int r0 = P.aptr[node], r1 = P.aptr[node + 1];
@@ -47,42 +46,9 @@ dense_back_kernel(const float* __restrict__ A, const BackParams P) {
             const float a = A[(long long)row * n + c];
             acc = (MODE == BACK_COLNORM2) ? fmaf(a, a, acc) : fmaf(a * prec, P.q[row], acc);
         }
-        if (MODE == BACK_PLAIN || MODE == BACK_COLNORM2) {
-            P.out[nb + c] = acc;
-        } else {
-            const float* __restrict__ v = P.v + nb;
-            const int ix = (int)(c / N), iy = (int)(c % N);
-            const float cv = v[c];
-            float lu = 0.f, ld = 0.f, ll = 0.f, lr = 0.f;   // same association as the projector's epilogue
-            if (ix >= 1) lu = cv - v[c - N];
-            if (ix + 1 < N) ld = cv - v[c + N];
-            if (iy >= 1) ll = cv - v[c - 1];
-            if (iy + 1 < N) lr = cv - v[c + 1];
-            const float lap = (lu + ld) + (ll + lr);
-            const float dd = P.rhoD_vec ? P.rhoD_vec[nb + c] : P.rhoD_s[node];
-            const float hv = acc + fmaf(dd, cv, P.mu * lap);
-            if (MODE == BACK_HP) {
-                P.out[nb + c] = hv;
-                dsum = cv * hv; dsum3 = hv * hv;
-            } else {
-                const float rr = (P.rhs0[nb + c] + P.tvterm[nb + c]) - hv;
-                P.out[nb + c] = rr;
-                P.p_out[nb + c] = rr;
-                dsum = rr * rr;
-            }
-        }
+        pixel_epilogue<MODE>(P, node, nb, c, acc, dsum, dsum3);
     }
-    if (MODE == BACK_HP) {
-        float vs[3] = {dsum, 0.f, dsum3};
-        block_sum<3>(vs, red);
-        grid_reduce_store<3>(vs, P.part + (long long)blockIdx.y * gridDim.x * 3, P.counter + blockIdx.y, blockIdx.x,
-                             gridDim.x, P.scal + (long long)node * NSCAL + P.dot_slot, red);
-    } else if (MODE == BACK_RESID0) {
-        float vs[1] = {dsum};
-        block_sum<1>(vs, red);
-        grid_reduce_store<1>(vs, P.part + (long long)blockIdx.y * gridDim.x, P.counter + blockIdx.y, blockIdx.x,
-                             gridDim.x, P.scal + (long long)node * NSCAL + P.dot_slot, red);
-    }
+    pixel_epilogue_reduce<MODE>(P, node, dsum, dsum3, red);
 }
 
 cudaError_t launch_dense_forward(const float* A, const int* anode, const FwdParams& P, int nodes, const FwdReduceParams& R,

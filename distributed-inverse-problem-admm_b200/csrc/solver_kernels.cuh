@@ -124,5 +124,9 @@ cudaError_t launch_accept(const AcceptParams& P, cudaStream_t st);
 cudaError_t launch_dense_forward(const float* A, const int* anode, const FwdParams& P, int nodes, const FwdReduceParams& R,
                                  cudaStream_t st);
 cudaError_t launch_dense_back(const float* A, int mode, const BackParams& P, int nodes, cudaStream_t st);
+// rotate-and-sum ("skimage-flavoured") projector variant (rotsum.cu): cs = (cos, sin) per angle row
+cudaError_t launch_rs_forward(const float2* cs, const int* anode, double det_w, const FwdParams& P, int nodes,
+                              const FwdReduceParams& R, cudaStream_t st);
+cudaError_t launch_rs_back(const float2* cs, double det_w, int mode, const BackParams& P, int nodes, cudaStream_t st);
 
 }  // namespace admm

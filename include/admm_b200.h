@@ -142,6 +142,11 @@ long long admm_plan_info(const admm_plan* plan, int what);
  * peer GPU's memory: a narrow grid keeps NVLink stores in flight beside HBM-bound kernels on another stream);
  * 0 (default): one block row per item. */
 #define ADMM_OPT_PACK_BLOCKS 0
+/* ADMM_OPT_IMPL: projector discretisation of the plan.  0 (default): Joseph (the hot path).  1: the
+ * "skimage-flavoured" rotate-and-sum variant of Gen_Sino_Partitioned.py:133 (`impl='skimage'`): bilinear ray marching on
+ * the rotated pixel grid with its exact transpose; plain kernels, admm_x_update then needs fuse_pupdate = 0.  Set it
+ * before asking ADMM_INFO_PART_FLOATS. */
+#define ADMM_OPT_IMPL 1
 int admm_plan_set(admm_plan* plan, int what, long long value);
 
 /* ---- K1 / K2 / K2b: the operator  (device pointers) ---------------------------------------------------

@@ -339,3 +339,86 @@ void orc_accum_cons(long n, double rho, const double* q, double qs, const double
 #pragma omp parallel for schedule(static)
     for (long k = 0; k < n; ++k) cons[k] += rho * (q ? q[k] : qs) * (z[k] - y[k]);
 }
+
+/* ==== (f)-2: "skimage-flavoured" rotate-and-sum projector (Gen_Sino_Partitioned.py:133 pins impl='skimage') ===========
+ * skimage.transform.radon(circle=False) rotates the sqrt(2)-padded image bilinearly and sums columns; ODL rescales to
+ * physical units.  Restated as ray marching on the rotated pixel grid: for detector bin j (centre s_j) and angle t the
+ * samples sit at  r_k = s_j (cos t, sin t) + t_k (-sin t, cos t),  t_k = (k - (P-1)/2) h,  k = 0..P-1,  P = ceil(sqrt2 N),
+ * the image is interpolated BILINEARLY there (zero outside), and the bin gets h * sum_k.  SURVEY App. C: this backend is
+ * "parity unpinned" (scikit-image / ODL are not installable here); the restatement brackets the discretisation
+ * ambiguity next to the Joseph contract.  power = 2: column norms^2. */
+static int rs_steps(int N) { return (int)ceil(sqrt(2.0) * N); }
+
+void orc_forward_rs(const double* X, int N, int D, double det_w, const double* cs, const double* sn, int nang,
+                    double* out) {
+    const double h = 2.0 / N, ds = det_w / D, smin = -0.5 * det_w, x0 = -1.0 + 0.5 * h;
+    const int P = rs_steps(N);
+#pragma omp parallel for collapse(2) schedule(dynamic, 16)
+    for (int a = 0; a < nang; ++a) {
+        for (int j = 0; j < D; ++j) {
+            const double c = cs[a], s = sn[a], sj = smin + (j + 0.5) * ds;
+            double acc = 0.0;
+            for (int k = 0; k < P; ++k) {
+                const double t = (k - 0.5 * (P - 1)) * h;
+                const double px = ((sj * c - t * s) - x0) / h, py = ((sj * s + t * c) - x0) / h;
+                const double fx0 = floor(px), fy0 = floor(py);
+                const long i0 = (long)fx0, j0 = (long)fy0;
+                const double fx = px - fx0, fy = py - fy0;
+                for (int di = 0; di < 2; ++di)
+                    for (int dj = 0; dj < 2; ++dj) {
+                        const long ii = i0 + di, jj = j0 + dj;
+                        if (ii < 0 || ii >= N || jj < 0 || jj >= N) continue;
+                        acc += (di ? fx : 1.0 - fx) * (dj ? fy : 1.0 - fy) * X[ii * N + jj];
+                    }
+            }
+            out[(long)a * D + j] = acc * h;
+        }
+    }
+}
+
+static void adjoint_rs_impl(const double* q, int N, int D, double det_w, const double* cs, const double* sn, int nang,
+                            int power, double* out) {
+    const double h = 2.0 / N, ds = det_w / D, smin = -0.5 * det_w, x0 = -1.0 + 0.5 * h, r = ds / h;
+    const int P = rs_steps(N);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int ix = 0; ix < N; ++ix)
+        for (int iy = 0; iy < N; ++iy) {
+            const double x = x0 + ix * h, y = x0 + iy * h;
+            double acc = 0.0;
+            for (int a = 0; a < nang; ++a) {
+                const double c = cs[a], s = sn[a];
+                /* (cos, sin) are fp32-rounded, so c^2 + s^2 = 1 + O(1e-7): the EXACT inverse of the forward's sample map
+                 * divides by it -- otherwise the gather is the transpose only to 1e-7 */
+                const double nrm2 = c * c + s * s;
+                const double tau = ((x * c + y * s) / nrm2 - smin) / ds - 0.5;     /* bin coordinate of the pixel centre */
+                const double kap = ((-x * s + y * c) / nrm2) / h + 0.5 * (P - 1);  /* step coordinate */
+                const double rad = 1.4142135623730951 + 1e-6;
+                long jlo = (long)ceil(tau - rad / r), jhi = (long)floor(tau + rad / r);
+                long klo = (long)ceil(kap - rad), khi = (long)floor(kap + rad);
+                if (jlo < 0) jlo = 0;
+                if (jhi > D - 1) jhi = D - 1;
+                if (klo < 0) klo = 0;
+                if (khi > P - 1) khi = P - 1;
+                for (long j = jlo; j <= jhi; ++j) {
+                    double wsum = 0.0;      /* A[(a, j), pixel] = h * sum_k (bilinear weight of sample (j, k) on the pixel) */
+                    for (long k = klo; k <= khi; ++k) {
+                        const double du = (j - tau) * r, dv = (double)k - kap;      /* offsets along u, u_perp in pixels */
+                        const double dx = du * c - dv * s, dy = du * s + dv * c;
+                        const double wx = 1.0 - fabs(dx), wy = 1.0 - fabs(dy);
+                        if (wx <= 0.0 || wy <= 0.0) continue;
+                        wsum += wx * wy;
+                    }
+                    wsum *= h;
+                    acc += (power == 2) ? wsum * wsum : wsum * q[(long)a * D + j];
+                }
+            }
+            out[(long)ix * N + iy] = acc;
+        }
+}
+
+void orc_adjoint_rs(const double* q, int N, int D, double det_w, const double* cs, const double* sn, int nang, double* out) {
+    adjoint_rs_impl(q, N, D, det_w, cs, sn, nang, 1, out);
+}
+void orc_colnorm2_rs(int N, int D, double det_w, const double* cs, const double* sn, int nang, double* out) {
+    adjoint_rs_impl(NULL, N, D, det_w, cs, sn, nang, 2, out);
+}

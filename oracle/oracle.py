@@ -56,6 +56,9 @@ def lib():
         L.orc_forward.argtypes = [_DP, i, i, d, _DP, _DP, i, _DP]
         L.orc_adjoint.argtypes = [_DP, i, i, d, _DP, _DP, i, _DP]
         L.orc_colnorm2.argtypes = [i, i, d, _DP, _DP, i, _DP]
+        L.orc_forward_rs.argtypes = [_DP, i, i, d, _DP, _DP, i, _DP]
+        L.orc_adjoint_rs.argtypes = [_DP, i, i, d, _DP, _DP, i, _DP]
+        L.orc_colnorm2_rs.argtypes = [i, i, d, _DP, _DP, i, _DP]
         L.orc_grad.argtypes = [_DP, i, _DP, _DP]
         L.orc_gradT.argtypes = [_DP, _DP, i, _DP]
         L.orc_div_reference.argtypes = [_DP, _DP, i, _DP]
@@ -153,7 +156,9 @@ def node_to_gpu(num_nodes: int, num_gpus: int) -> list:
 class JosephOperator:
     """Matrix-free A_i: (N,N) image -> (M_i, D) sinogram, with .T and column norms."""
 
-    def __init__(self, N, theta, D=None, det_w=2.0):
+    def __init__(self, N, theta, D=None, det_w=2.0, impl="joseph"):
+        """impl: "joseph" (the canonical contract) or "skimage" (rotate-and-sum with bilinear
+        interpolation, the backend Gen_Sino_Partitioned.py:133 pins; see admm_oracle.c orc_forward_rs)."""
         self.N = int(N)
         self.D = int(D if D is not None else N)
         self.det_w = float(det_w)
@@ -161,22 +166,28 @@ class JosephOperator:
         self.c, self.s = trig_table(self.theta)
         self.nang = len(self.theta)
         self.shape = (self.nang * self.D, self.N * self.N)
+        if impl not in ("joseph", "skimage"):
+            raise ValueError(impl)
+        self.impl = impl
 
     def forward(self, x):
         x = _f64(np.asarray(x).reshape(-1))
         out = np.empty(self.nang * self.D)
-        lib().orc_forward(_p(x), self.N, self.D, self.det_w, _p(self.c), _p(self.s), self.nang, _p(out))
+        fn = lib().orc_forward if self.impl == "joseph" else lib().orc_forward_rs
+        fn(_p(x), self.N, self.D, self.det_w, _p(self.c), _p(self.s), self.nang, _p(out))
         return out
 
     def adjoint(self, q):
         q = _f64(np.asarray(q).reshape(-1))
         out = np.empty(self.N * self.N)
-        lib().orc_adjoint(_p(q), self.N, self.D, self.det_w, _p(self.c), _p(self.s), self.nang, _p(out))
+        fn = lib().orc_adjoint if self.impl == "joseph" else lib().orc_adjoint_rs
+        fn(_p(q), self.N, self.D, self.det_w, _p(self.c), _p(self.s), self.nang, _p(out))
         return out
 
     def colnorm2(self):
         out = np.empty(self.N * self.N)
-        lib().orc_colnorm2(self.N, self.D, self.det_w, _p(self.c), _p(self.s), self.nang, _p(out))
+        fn = lib().orc_colnorm2 if self.impl == "joseph" else lib().orc_colnorm2_rs
+        fn(self.N, self.D, self.det_w, _p(self.c), _p(self.s), self.nang, _p(out))
         return out
 
     def __matmul__(self, x):
@@ -202,6 +213,31 @@ class _Transposed:
 
     def __matmul__(self, q):
         return self.op.adjoint(q)
+
+
+def np_forward_rs(X, c, s, D, det_w=2.0):
+    """Pure-NumPy twin of orc_forward_rs: rotate-and-sum with bilinear interpolation (literal statement)."""
+    X = np.asarray(X, dtype=np.float64)
+    N = X.shape[0]
+    h, ds, smin, x0 = 2.0 / N, det_w / D, -0.5 * det_w, -1.0 + 1.0 / N
+    P = int(math.ceil(math.sqrt(2.0) * N))
+    sj = smin + (np.arange(D) + 0.5) * ds
+    tk = (np.arange(P) - 0.5 * (P - 1)) * h
+    out = np.zeros((len(c), D))
+    Xp = np.zeros((N + 2, N + 2))
+    Xp[1:-1, 1:-1] = X                      # zero ring: taps outside the image contribute 0
+    for a, (ca, sa) in enumerate(zip(c, s)):
+        px = ((sj[:, None] * ca - tk[None, :] * sa) - x0) / h
+        py = ((sj[:, None] * sa + tk[None, :] * ca) - x0) / h
+        i0, j0 = np.floor(px).astype(np.int64), np.floor(py).astype(np.int64)
+        fx, fy = px - i0, py - j0
+        acc = np.zeros_like(px)
+        for di, wx in ((0, 1.0 - fx), (1, fx)):
+            for dj, wy in ((0, 1.0 - fy), (1, fy)):
+                ii, jj = np.clip(i0 + di + 1, 0, N + 1), np.clip(j0 + dj + 1, 0, N + 1)
+                acc += wx * wy * Xp[ii, jj]
+        out[a] = acc.sum(axis=1) * h
+    return out
 
 
 def np_forward(X, c, s, D, det_w=2.0):

@@ -76,8 +76,10 @@ def test_block2_block3_gen_sino_against_oracle():
     G, Wl, Qm, keep = b3.build_pixel_connected_Q_provider(A_dense_list=data["A_dense_list"], strategy="ring")
     assert G.number_of_nodes() == V and keep is None
     # generate_sinogram
+    # generate_sinogram pins impl='skimage' (Gen_Sino_Partitioned.py:133): the rotate-and-sum variant
     noisy, rt, geom, space, A = gs.generate_sinogram(O.shepp_logan(48), np.zeros(30))
-    ref = O.JosephOperator(48, (np.arange(30) + 0.5) * np.pi / 30)
+    ref = O.JosephOperator(48, (np.arange(30) + 0.5) * np.pi / 30, impl="skimage")
+    assert rt.impl == "skimage"
     assert _rel(noisy.asarray(), ref.forward(O.shepp_logan(48))) < 1e-4 and A.shape == (30 * 48, 48 * 48)
 
 
@@ -256,3 +258,49 @@ def test_dense_ndarray_operators_accepted_like_the_reference():
                                 [np.ones(N * N)])
     pr.solve(eps=1e-6, max_iters=200)
     assert _rel(xi.value, xr.value) < 1e-3 and abs(prob.value - pr.value) < 1e-3 * abs(pr.value)
+
+
+@pytest.mark.parametrize("N,M,D,det_w", [(48, 30, None, 2.0), (37, 11, 50, 2.6), (128, 45, None, 2.0)])
+def test_skimage_flavoured_projector_vs_oracle(N, M, D, det_w):
+    """(f)-2: `impl="skimage"` (Gen_Sino_Partitioned.py:133) is the rotate-and-sum bilinear projector with its exact
+    transpose -- forward, adjoint and column norms against the fp64 oracle (<= 1e-4 relative L2), adjointness, and how
+    far it sits from the Joseph contract (the bracket of SURVEY App. C)."""
+    from admm_b200 import RayTransformCUDA
+    from oracle import oracle as O
+    theta = (np.arange(M) + 0.5) * np.pi / M
+    op = RayTransformCUDA(N, theta, D, det_w, impl="skimage")
+    ref = O.JosephOperator(N, theta, D, det_w, impl="skimage")
+    rng = np.random.default_rng(3)
+    x = O.shepp_logan(N) + 0.05 * rng.standard_normal((N, N))
+    y = op @ x.reshape(-1)
+    assert _rel(y, ref.forward(x)) < 1e-4
+    q = rng.standard_normal(op.shape[0])
+    assert _rel(op.T @ q, ref.adjoint(q)) < 1e-4
+    assert _rel(op.colnorm2(), ref.colnorm2()) < 1e-4
+    lhs, rhs = float(y @ q), float(x.reshape(-1) @ (op.T @ q))
+    assert abs(lhs - rhs) <= 1e-6 * float(np.linalg.norm(y) * np.linalg.norm(q))
+    jos = RayTransformCUDA(N, theta, D, det_w) @ O.shepp_logan(N).reshape(-1)
+    rs = op @ O.shepp_logan(N).reshape(-1)
+    assert 1e-4 < _rel(rs, jos) < 5e-2          # two discretisations of the same integrals: close, not equal
+
+
+def test_admm_with_skimage_flavoured_operators():
+    """The solver runs unchanged on the rotate-and-sum variant (plain kernels behind the same operator contract)."""
+    from admm_b200 import RayTransformCUDA, node_angles
+    from block_6_admm_loop_ver2 import decentralized_admm
+    from oracle import oracle as O
+    N, M, V, iters = 32, 48, 3, 10
+    thetas = node_angles(M, V)
+    img = O.shepp_logan(N)
+    ops_o = [O.JosephOperator(N, t, impl="skimage") for t in thetas]
+    sinos = [(op.forward(img) + 0.005 * np.random.default_rng(9 + i).standard_normal(op.shape[0]))
+             .reshape(op.nang, N).astype(np.float32) for i, op in enumerate(ops_o)]
+    G = O.make_graph("complete", V)
+    kw = dict(lam_tv=0.02, rho=2.0, max_iters=iters, eps_pri=0.0, eps_dual=0.0, phantom_true=img)
+    xo, ho = O.decentralized_admm(ops_o, sinos, G, None, None, N, uniform_q=1.0, x_update_fn=O.np_x_update, **kw)
+    xg, hg = decentralized_admm([RayTransformCUDA(N, t, impl="skimage") for t in thetas], sinos, G, None, None, N,
+                                verbose=False, **kw)
+    assert np.allclose(hg["primal"], ho["primal"], rtol=1e-3) and np.allclose(hg["dual"], ho["dual"], rtol=1e-3)
+    assert np.array_equal(np.array(hg["tighten_history"]), np.array(ho["tighten_history"]))
+    for i in range(V):
+        assert _rel(xg[i], xo[i]) < 1e-3
