@@ -14,7 +14,7 @@ _ROOT = os.path.dirname(_PKG)                      # distributed-inverse-problem
 CSRC = os.path.join(_ROOT, "csrc")
 LIB_PATH = os.path.join(_ROOT, "libadmm_b200.so")
 HEADER = os.path.join(os.path.dirname(_ROOT), "include", "admm_b200.h")
-SOURCES = ["api.cu", "projector.cu", "solver_kernels.cu", "tv_helpers.cu", "dense.cu", "rotsum.cu"]
+SOURCES = ["api.cu", "projector.cu", "solver_kernels.cu", "tv_helpers.cu", "dense.cu", "rotsum.cu", "pixel_masks.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -102,6 +102,8 @@ def lib():
     L.admm_tv_pass.argtypes = [vp, ctypes.POINTER(State), i, i, i, vp]
     L.admm_accept.argtypes = [vp, ctypes.POINTER(State), i, i, d, i, i, vp]
     L.admm_edge_update.argtypes = [vp, ctypes.POINTER(State), vp, i, vp, vp]
+    L.admm_pixel_masks.argtypes = [i, ll, i, i, i, vp, vp, vp, vp]
+    L.admm_pixel_masks.restype = i
     L.admm_pack.argtypes = [vp, vp, i, vp]
     L.admm_push_copy.argtypes = [vp, vp, i, vp]
     L.admm_finalize.argtypes = [vp, ctypes.POINTER(State), vp, vp, vp, vp, i, i, vp, vp, vp, vp, i, vp, vp]
@@ -127,7 +129,7 @@ def lib():
 EXPORTS = ("admm_version", "admm_abi_sizeof", "admm_last_error", "admm_device_count", "admm_plan_create",
            "admm_plan_create_dense", "admm_plan_upload_dense", "admm_plan_destroy",
            "admm_plan_info", "admm_plan_set", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host",
-           "admm_adjoint_host", "admm_colnorm2_host", "admm_rhs0", "admm_x_update", "admm_edge_update", "admm_pack", "admm_push_copy", "admm_finalize",
+           "admm_adjoint_host", "admm_colnorm2_host", "admm_rhs0", "admm_x_update", "admm_edge_update", "admm_pack", "admm_push_copy", "admm_finalize", "admm_pixel_masks",
            "admm_tv_pass", "admm_accept", "admm_launch_count", "admm_profile_enable", "admm_profile_read", "admm_grad2d_host",
            "admm_div2d_host", "admm_kt_subgrad_host", "admm_ipc_alloc", "admm_ipc_open", "admm_ipc_close", "admm_ipc_free")
 

@@ -101,6 +101,37 @@ def _build_all_pixel_masks(q_cache, num_nodes, n, strategy="knn", k=2, seed=0):
     return keep
 
 
+def _build_all_pixel_masks_device(Wi_list, q_mode, num_nodes, n, strategy="knn", k=2, seed=0, device=0):
+    """The same keep[V, V, n] built on the GPU (csrc/pixel_masks.cu, C ABI `admm_pixel_masks`): one thread per pixel,
+    q_ij[p] formed from the W vectors in float32 exactly like make_precisions, Kruskal in networkx's edge order, bit
+    rows unpacked here.  Needs Q to be make_precisions' own provider (so that q_ij is a function of W) and V <= 32; the
+    `chain` permutations are drawn on the host from np.random.default_rng(seed) pixel by pixel like the reference."""
+    import ctypes
+    import torch
+    from admm_b200 import _native as nat
+    nat.require_cuda()
+    if num_nodes > 32:
+        raise ValueError("the device mask builder packs a node's row into 32 bits (V <= 32)")
+    if num_nodes * num_nodes * n > 2 ** 28:
+        raise MemoryError("per-pixel masks are a small-problem option (V*V*n bools); use a node-level strategy")
+    dev = torch.device(f"cuda:{device}")
+    strat = {"knn": 0, "mst": 1, "chain": 2}[strategy]
+    W = perm = None
+    if strat == 2:
+        rng = np.random.default_rng(seed)
+        perm = torch.from_numpy(np.stack([rng.permutation(num_nodes) for _ in range(n)]).astype(np.uint8)).to(dev)
+    else:
+        W = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(w, dtype=np.float32).reshape(-1)
+                                                           for w in Wi_list]))).to(dev)
+    bits = torch.zeros(num_nodes, n, dtype=torch.int32, device=dev)
+    nat.check(nat.lib().admm_pixel_masks(num_nodes, n, strat, int(k), 1 if q_mode == "harmonic" else 0,
+                                         W.data_ptr() if W is not None else None,
+                                         perm.data_ptr() if perm is not None else None, bits.data_ptr(),
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "admm_pixel_masks")
+    b = bits.cpu().numpy().view(np.uint32)                                   # [V][n], bit j of row i = keep[i, j, p]
+    return ((b[:, None, :] >> np.arange(num_nodes, dtype=np.uint32)[None, :, None]) & 1).astype(bool)
+
+
 def _union_graph(keep):
     """block_3_graph_and_precisions.py:201-206: node graph with an edge wherever any pixel keeps the pair."""
     V = keep.shape[0]
@@ -115,12 +146,15 @@ def _union_graph(keep):
 
 def build_pixel_connected_Q_provider(base_dir="saved_operators_Incmp_Span", A_dense_list_pickle="A_dense_list.pkl",
                                      strategy="knn", k=2, seed=0, q_mode="arithmetic", verbose=True, plot_union=True,
-                                     show_plots=False, output_dir="pixel_graphs_out", A_dense_list=None, p=0.1):
+                                     show_plots=False, output_dir="pixel_graphs_out", A_dense_list=None, p=0.1,
+                                     mask_device="auto"):
     """block_3_graph_and_precisions.py:262-319.  Returns (G_union, Wi_list, Qij_diag_masked, keep).
 
     `A_dense_list` (list of operators) replaces the pickle the reference loads (:288-291); if it is None the pickle
     path is tried.  Node-level strategies return `keep=None` and an unmasked provider; per-pixel strategies behave
-    like the reference.  Unlike the reference (:304-309) a graph is always returned."""
+    like the reference.  Unlike the reference (:304-309) a graph is always returned.
+    `mask_device`: "auto" (GPU mask builder when a device is present and V <= 32, else the host restatement),
+    "device", "host"."""
     if A_dense_list is None:
         import os
         import pickle
@@ -144,8 +178,19 @@ def build_pixel_connected_Q_provider(base_dir="saved_operators_Incmp_Span", A_de
             return Qij_diag(i, j)
         Qij_diag_masked._admm_b200_spec = Qij_diag._admm_b200_spec
         return G, Wi_list, Qij_diag_masked, None
-    q_cache = _precompute_q_cache(V, Qij_diag)
-    keep = _build_all_pixel_masks(q_cache, V, n, strategy=strategy, k=k, seed=seed)
+    keep = None
+    if V <= 32 and mask_device != "host":
+        # per-pixel graph work on the GPU (the reference's Python loop over pixels with networkx is its second hot loop,
+        # SURVEY 3.1); falls back to the host restatement only when there is no CUDA device and "auto" was asked
+        try:
+            keep = _build_all_pixel_masks_device(Wi_list, q_mode, V, n, strategy=strategy, k=k, seed=seed)
+        except RuntimeError:
+            if mask_device == "device":
+                raise
+    q_cache = _LazyQ(Qij_diag)
+    if keep is None:
+        q_cache = _precompute_q_cache(V, Qij_diag)
+        keep = _build_all_pixel_masks(q_cache, V, n, strategy=strategy, k=k, seed=seed)
     G_union = _union_graph(keep)
 
     def Qij_diag_masked(i, j):  # :312-317
@@ -153,3 +198,15 @@ def build_pixel_connected_Q_provider(base_dir="saved_operators_Incmp_Span", A_de
             return np.zeros(n, dtype=float)
         return np.where(keep[i, j, :], q_cache[(i, j)], 0.0)
     return G_union, Wi_list, Qij_diag_masked, keep
+
+
+class _LazyQ(dict):
+    """q_cache[(i, j)] evaluated on first use (the device mask builder does not need the V^2 host vectors)."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self._fn = fn
+
+    def __missing__(self, key):
+        self[key] = self._fn(*key)
+        return self[key]

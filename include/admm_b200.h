@@ -228,6 +228,15 @@ int admm_grad2d_host(int N, const double* h_x, double* h_gx, double* h_gy);
 int admm_div2d_host(int N, const double* h_px, const double* h_py, int exact_adjoint, double* h_out);
 int admm_kt_subgrad_host(int N, const double* h_x, double eps, int exact_adjoint, double* h_out, double* h_mag);
 
+/* ---- per-pixel graph masks   block_3_graph_and_precisions.py:62-187 (_pixel_mask_knn_then_connect, _pixel_mask_mst,
+ * _pixel_mask_chain, _build_all_pixel_masks) ---------------------------------------------------------------------------
+ * One thread per pixel.  d_W[V][n]: make_precisions' W vectors (float32); q_ij[p] = 0.5 (W_i + W_j) or, `harmonic`,
+ * W_i W_j / (W_i + W_j), floored at 1e-12, in float32 like the reference (:27-39).  strategy 0 knn (k neighbours, plus the
+ * maximum-spanning-tree edges when not connected), 1 mst (Kruskal in networkx's edge order), 2 chain (d_perm[n][V]
+ * uint8 permutations drawn by the host).  d_keep_bits[V][n]: bit j of word [i][p] = keep[i, j, p]; V <= 32. */
+int admm_pixel_masks(int V, long long n, int strategy, int k, int harmonic, const float* d_W,
+                     const unsigned char* d_perm, unsigned* d_keep_bits, void* stream);
+
 /* launches issued by this library since load (the bench's gpu_launches evidence) */
 long long admm_launch_count(void);
 

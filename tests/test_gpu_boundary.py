@@ -304,3 +304,36 @@ def test_admm_with_skimage_flavoured_operators():
     assert np.array_equal(np.array(hg["tighten_history"]), np.array(ho["tighten_history"]))
     for i in range(V):
         assert _rel(xg[i], xo[i]) < 1e-3
+
+
+def test_device_pixel_masks_bit_exact_vs_reference_fixture():
+    """(f)-1: the per-pixel kNN / MST / chain masks of block_3_graph_and_precisions.py:62-187 built on the device
+    (bit-packed, one thread per pixel) equal, bit for bit, what the REFERENCE's own code produced (fixture written by
+    tests/golden/make_golden.py executing block_3._build_all_pixel_masks) and the host restatement on a larger case."""
+    import os
+    import block_3_graph_and_precisions as b3
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.npz"))
+    A = list(gold["b3_A"])
+    V, n = len(A), A[0].shape[1]
+    for mode in ("arithmetic", "harmonic"):
+        Wi, Q = b3.make_precisions(A, q_mode=mode)
+        for strat in ("knn", "mst", "chain"):
+            keep = b3._build_all_pixel_masks_device(Wi, mode, V, n, strategy=strat, k=2, seed=123)
+            assert keep.dtype == bool and keep.shape == (V, V, n)
+            assert np.array_equal(keep, gold[f"b3_keep_{mode}_{strat}"]), (mode, strat)
+    # a larger random case against the host restatement (networkx), incl. k = 1 (forces the spanning-tree repair)
+    rng = np.random.default_rng(11)
+    V, n = 9, 700
+    Wl = [rng.random(n).astype(np.float32) + 0.01 for _ in range(V)]
+    for mode in ("arithmetic", "harmonic"):
+        Wi, Q = b3.make_precisions(Wl, q_mode=mode)            # 1-D entries are taken as W vectors
+        qc = b3._precompute_q_cache(V, Q)
+        for strat, k in (("knn", 1), ("knn", 3), ("mst", 0), ("chain", 0)):
+            host = b3._build_all_pixel_masks(qc, V, n, strategy=strat, k=k, seed=5)
+            dev = b3._build_all_pixel_masks_device(Wi, mode, V, n, strategy=strat, k=k, seed=5)
+            assert np.array_equal(host, dev), (mode, strat, k)
+    # and through the public entry point
+    G, Wi, Qm, keep = b3.build_pixel_connected_Q_provider(A_dense_list=A, strategy="knn", k=2, seed=123,
+                                                          q_mode="arithmetic", mask_device="device")
+    assert np.array_equal(keep, gold["b3_keep_arithmetic_knn"])
+    assert np.array_equal(Qm(0, 1), np.where(keep[0, 1], b3.make_precisions(A)[1](0, 1), 0.0))
