@@ -291,18 +291,15 @@ def inner_accuracy(S, C, acceptance):
 
 
 def workload_config(args, cfg, G):
-    c = {"workload": f"{args.config}: {cfg['desc']}", "N": cfg["N"], "angles": cfg["M"], "nodes": total_nodes(cfg),
-         "graph": cfg["graph"], "lam_tv": LAM, "rho": RHO, "tv_mu": RHO, "tv_sweeps": args.tv_sweeps,
-         "cg_iters": args.cg_iters, "acceptance": bool(getattr(args, "acceptance", 0)), "noise_sigma": SIGMA,
-         "partition": "single GPU" if args.gpus == 1 else getattr(args, "partition_used", args.partition),
-         "inputs_larger_than_L2": cfg["N"] >= 1024 or total_nodes(cfg) * cfg["N"] ** 2 * 4 * 10 > 126e6,
-         "stop_test": "disabled in the timed region",
-         "inner_accuracy": inner_accuracy(args.tv_sweeps, args.cg_iters, bool(getattr(args, "acceptance", 0)))}
-    if args.gpus > 1:
-        c["parallelism"] = f"graph nodes sharded over {args.gpus} GPUs, cut-edge exchange={getattr(args, 'exchange_used', args.exchange)}" + (f" in {args.phases_used} phases" if getattr(args, "phases_used", 1) > 1 else "")
-    if G is not None:
-        c["edges"] = G.number_of_edges()
-    return c
+    """The declared workload -- identical in the `ours` and `reference` arms (what was asked for, not what a run found:
+    the node map / exchange path a sharded run ended up with are reported beside it under `parallelism`)."""
+    return {"workload": f"{args.config}: {cfg['desc']}", "N": cfg["N"], "angles": cfg["M"], "nodes": total_nodes(cfg),
+            "graph": cfg["graph"], "edges": G.number_of_edges(), "lam_tv": LAM, "rho": RHO, "tv_mu": RHO,
+            "tv_sweeps": args.tv_sweeps, "cg_iters": args.cg_iters, "acceptance": bool(args.acceptance),
+            "noise_sigma": SIGMA, "gpus": args.gpus, "partition": args.partition, "exchange": args.exchange,
+            "inputs_larger_than_L2": cfg["N"] >= 1024 or total_nodes(cfg) * cfg["N"] ** 2 * 4 * 10 > 126e6,
+            "stop_test": "disabled in the timed region",
+            "inner_accuracy": inner_accuracy(args.tv_sweeps, args.cg_iters, bool(args.acceptance))}
 
 
 def main():
@@ -378,7 +375,7 @@ def main():
         from admm_b200.sharding import cut_statistics
         cs = cut_statistics(G, world, eng.node_rank)
         contiguous = eng.node_rank == [(i * world) // len(eng.node_rank) for i in range(len(eng.node_rank))]
-        args.partition_used = ("contiguous" if contiguous else "balanced min-cut") + f" ({cs['cut']} of {cs['edges']} edges cut, max {max(cs['per_rank_ends'])} ends on a rank)"
+        args.partition_used = ("contiguous" if contiguous else "balanced min-cut, angle-balanced") + f" ({cs['cut']} of {cs['edges']} edges cut, max {max(cs['per_rank_ends'])} ends on a rank)"
 
     def barrier():
         if world > 1:
@@ -551,6 +548,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg, G),
+                "parallelism": (None if world == 1 else {"node_map": getattr(args, "partition_used", None),
+                                                        "exchange": getattr(args, "exchange_used", None),
+                                                        "phases": getattr(args, "phases_used", 1)}),
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
                 "launch_mode": ("CUDA-graph replay of the outer iteration (launch count = kernel nodes replayed)" if graph_replay
                                 else "eager launches (per-kernel CUDA events ride in the timed region)"),
