@@ -1,21 +1,24 @@
-# ncu evidence for profiles/ (one GPU).  Run only after the same command has exited 0 without ncu.
+# ncu evidence for profiles/ (one GPU).  Each ncu pass runs only after the same command exited 0 without ncu.
 # usage: tools/ncu_capture.sh <tag> [launches] [proj] [stream]
+# One warm outer iteration of the default bench (cfg4, 1 sweep x 2 CG per solve, a14 rule on: 3 solves) is 37 launches:
+# rhs0, 3 x (back<2>, fwd, reduce, back<1>, axpy, fwd(fused), reduce, back<1>, axpy, cg_update, tv), sino_resid, edge, finalize.
 set -e
 TAG=$1; shift
-CMD="python bench.py --config cfg4 --steps 1 --no-cpu --no-e2e --no-profile"
+export ADMM_B200_NOGRAPH=1     # eager launches, so that -s / -c count kernels of the bench loop itself
+CMD="python bench.py --config cfg4 --steps 1 --warmup 3 --no-cpu --no-e2e --no-profile"
 $CMD > gpurun_out/plain.log 2>&1
 for what in "$@"; do
   if [ "$what" = "launches" ]; then
-    ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 44 --csv --log-file gpurun_out/${TAG}_launches_cfg4.csv $CMD > gpurun_out/ncu1.log 2>&1
+    ncu --metrics gpu__time_duration.sum --clock-control none -s 116 -c 37 --csv --log-file gpurun_out/${TAG}_launches_cfg4.csv $CMD > gpurun_out/ncu1.log 2>&1
   fi
   if [ "$what" = "proj" ]; then
-    # filtered launch order in a warm iteration: fwd (plain), back<2>, [fwd (plain) back<1>], fwd (CG-fused), back<1>, ...
-    ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:"fwd_strip|back_tile_kernelILi1" -s 34 -c 3 -f -o gpurun_out/${TAG}_cfg4_proj $CMD > gpurun_out/ncu2.log 2>&1
+    # projector launches of the 4th iteration in order: back<2>, fwd, back<1>, fwd (CG-fused), back<1>  (x3 solves)
+    ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:"fwd_strip|back_tile_kernelILi[12]" -s 47 -c 5 -f -o gpurun_out/${TAG}_cfg4_proj $CMD > gpurun_out/ncu2.log 2>&1
     ncu -i gpurun_out/${TAG}_cfg4_proj.ncu-rep --page raw --csv > gpurun_out/${TAG}_cfg4_proj_raw.csv
   fi
   if [ "$what" = "stream" ]; then
-    ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:"tv_fused|edge_kernel|rhs0_kernel|cg_update" -s 12 -c 4 -f -o gpurun_out/${TAG}_cfg4_stream $CMD > gpurun_out/ncu3.log 2>&1
+    ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:"tv_fused|edge_kernel|rhs0_kernel|cg_update" -s 24 -c 8 -f -o gpurun_out/${TAG}_cfg4_stream $CMD > gpurun_out/ncu3.log 2>&1
     ncu -i gpurun_out/${TAG}_cfg4_stream.ncu-rep --page raw --csv > gpurun_out/${TAG}_cfg4_stream_raw.csv
   fi
 done
-ls -la gpurun_out/
+ls -la gpurun_out/ | tail -12
