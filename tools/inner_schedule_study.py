@@ -113,7 +113,16 @@ def main():
     for cname in args.configs.split(","):
         cfg = CONFIGS[cname]
         V, N = cfg["V"], cfg["N"]
-        xr, hr, cr, tr, img = run(cfg, args.iters, REF_S, REF_C, False, REF_MU)
+        # the reference run is the expensive part: cached next to the output (not committed)
+        cache = os.path.join(os.path.dirname(args.out), f"_study_ref_{cname}_{args.iters}.npz")
+        if os.path.exists(cache):
+            z = np.load(cache, allow_pickle=True)
+            xr, hr, tr, img = list(z["x"]), z["h"].item(), float(z["t"]), z["img"]
+            cr = Counting()
+            cr.cg, cr.sweeps = REF_S * REF_C * V * args.iters, REF_S * V * args.iters
+        else:
+            xr, hr, cr, tr, img = run(cfg, args.iters, REF_S, REF_C, False, REF_MU)
+            np.savez_compressed(cache, x=np.stack(xr), h=np.array(hr, dtype=object), t=tr, img=img)
         pr, dr = np.array(hr["primal"]), np.array(hr["dual"])
         res = out.setdefault(cname, {})
         res["_config"] = {k: (v if not isinstance(v, tuple) else list(v)) for k, v in cfg.items()}
