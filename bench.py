@@ -322,7 +322,7 @@ def main():
     ap.add_argument("--acceptance", type=int, default=1, choices=[0, 1],
                     help="1: the reference's accept / tighten-and-retry rule (block_6_ver2:100-176) on the device: up to "
                          "3 solves of tv_sweeps x cg_iters per node and iteration")
-    ap.add_argument("--carry", default="off", choices=["iteration", "always", "off"],
+    ap.add_argument("--carry", default="off", choices=["first_retry", "iteration", "always", "off"],
                     help="CG residual between solves: rebuilt by a back-projection at every solve (default), carried by "
                          "the TV pass within an outer iteration, or across iterations too (both keep the fp32 recurrence "
                          "residual: trace error vs the oracle 1e-3 .. 6e-3 instead of 4e-6)")

@@ -14,7 +14,7 @@ _ROOT = os.path.dirname(_PKG)                      # distributed-inverse-problem
 CSRC = os.path.join(_ROOT, "csrc")
 LIB_PATH = os.path.join(_ROOT, "libadmm_b200.so")
 HEADER = os.path.join(os.path.dirname(_ROOT), "include", "admm_b200.h")
-SOURCES = ["api.cu", "projector.cu", "solver_kernels.cu", "tv_helpers.cu", "dense.cu", "rotsum.cu", "pixel_masks.cu"]
+SOURCES = ["api.cu", "projector.cu", "solver_kernels.cu", "tv_helpers.cu", "dense.cu", "rotsum.cu", "pixel_masks.cu", "tma.cu", "pdhg.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -114,6 +114,14 @@ def lib():
     L.admm_ipc_open.argtypes = [vp, ctypes.POINTER(vp)]
     L.admm_ipc_close.argtypes = [vp]
     L.admm_ipc_free.argtypes = [vp]
+    f = ctypes.c_float
+    L.admm_pdhg_dual.argtypes = [vp, vp, ll, vp, vp, vp, vp, vp, f, f, i, i, vp]
+    L.admm_pdhg_primal.argtypes = [vp, vp, vp, ll, vp, vp, vp, vp, vp, f, f, i, i, vp]
+    L.admm_pdhg_normal.argtypes = [vp, vp, ll, vp, vp, vp, i, i, vp]
+    L.admm_pdhg_combine.argtypes = [vp, vp, ll, vp, vp, vp, i, vp]
+    L.admm_pdhg_sums.argtypes = [vp, vp, ll, vp, vp, vp, vp, i, i, vp]
+    for name in ("admm_pdhg_dual", "admm_pdhg_primal", "admm_pdhg_normal", "admm_pdhg_combine", "admm_pdhg_sums"):
+        getattr(L, name).restype = i
     L.admm_profile_enable.argtypes = [i]
     L.admm_profile_read.argtypes = [vp, vp]
     for name in ("admm_ipc_alloc", "admm_ipc_open", "admm_ipc_close", "admm_ipc_free", "admm_grad2d_host", "admm_div2d_host", "admm_kt_subgrad_host", "admm_profile_enable", "admm_profile_read", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host", "admm_adjoint_host",
@@ -131,7 +139,8 @@ EXPORTS = ("admm_version", "admm_abi_sizeof", "admm_last_error", "admm_device_co
            "admm_plan_info", "admm_plan_set", "admm_forward", "admm_adjoint", "admm_colnorm2", "admm_forward_host",
            "admm_adjoint_host", "admm_colnorm2_host", "admm_rhs0", "admm_x_update", "admm_edge_update", "admm_pack", "admm_push_copy", "admm_finalize", "admm_pixel_masks",
            "admm_tv_pass", "admm_accept", "admm_launch_count", "admm_profile_enable", "admm_profile_read", "admm_grad2d_host",
-           "admm_div2d_host", "admm_kt_subgrad_host", "admm_ipc_alloc", "admm_ipc_open", "admm_ipc_close", "admm_ipc_free")
+           "admm_div2d_host", "admm_kt_subgrad_host", "admm_ipc_alloc", "admm_ipc_open", "admm_ipc_close", "admm_ipc_free",
+           "admm_pdhg_dual", "admm_pdhg_primal", "admm_pdhg_normal", "admm_pdhg_combine", "admm_pdhg_sums")
 
 OPT_PACK_BLOCKS = 0
 OPT_IMPL = 1

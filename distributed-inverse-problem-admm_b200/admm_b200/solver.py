@@ -63,10 +63,13 @@ class ADMMEngine:
         # back-projection.  "iteration": only the first solve of an outer iteration does, later sweeps / a14 retry solves
         # take the r the TV pass carried along (r += tvterm' - tvterm); "always": also across iterations (the rhs0
         # assembly carries it; rebuilt every ax_refresh_every iterations).  Carrying saves 1.7 ms per solve at cfg 4 but
-        # keeps the fp32 CG-recurrence residual instead of the true one: measured 200-iteration trace error vs the
-        # oracle 1e-3 ("iteration") and 2e-4..6e-3 ("always") instead of 4e-6 -- at north_star's tolerance, so off
-        if carry_residual not in ("iteration", "always", False, None):
-            raise ValueError(f"carry_residual must be 'iteration', 'always' or False, not {carry_residual!r}")
+        # keeps the fp32 CG-recurrence residual instead of the true one: measured 200-iteration trace error vs
+        # the fp64 oracle 1e-3 ("iteration") and 2e-4..6e-3 ("always") instead of 4e-6 -- at north_star's tolerance, so off
+        # "first_retry": only the a14 rule's FIRST retry solve takes the carried residual; the last solve of an iteration
+        # always rebuilds it, so whatever the carried one missed is seen (and corrected) before x leaves the iteration
+        if carry_residual not in ("first_retry", "iteration", "always", False, None):
+            raise ValueError("carry_residual must be 'first_retry', 'iteration', 'always' or False, "
+                             f"not {carry_residual!r}")
         self.carry_r = carry_residual or False
         self.dist, self.rank, self.world, self.group = dist, int(rank), int(world), group
         self._G = G
@@ -533,6 +536,8 @@ class ADMMEngine:
                 st.masked, st.reuse_ax, st.reuse_r, st.accept_mode = 1, 1, st.carry_r, 2
                 for t in range(self.max_tighten):
                     last = (t == self.max_tighten - 1)
+                    if self.carry_r == "first_retry":
+                        st.reuse_r = 1 if (t == 0 and not last) else 0
                     # sharded: x is final after the LAST retry's CG, so its TV pass (w, tvterm, |g| only) is held back and
                     # runs under the cut-edge exchange (tv_phase); needs the whole rank in one node group
                     st.defer_tv = 1 if (self._defer_last_tv and last) else 0

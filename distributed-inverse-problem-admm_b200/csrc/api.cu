@@ -379,7 +379,7 @@ static BackParams make_back(const admm_plan* p, const float* q, const float* pre
                             int node0) {
     BackParams B{};
     B.q = q; B.ang = p->d_ang; B.aptr = p->d_aptr; B.prec = prec; B.out = out; B.stride = stride;
-    B.node0 = node0; B.N = p->N; B.D = p->D; B.bspan = p->bspan;
+    B.node0 = node0; B.N = p->N; B.D = p->D; B.bspan = p->bspan; B.A_rows = p->A;
     return B;
 }
 
@@ -657,6 +657,49 @@ extern "C" int admm_finalize(admm_plan* p, const admm_state* s, const double* d_
     F.ctl = reinterpret_cast<const NodeCtl*>(s->ctl);
     F.iter_dev = s->iter_dev; F.hist_stride = s->hist_stride;
     CK(launch_finalize(F, (cudaStream_t)stream));
+    return ADMM_OK;
+}
+
+// ---- PDHG consensus variant (ADMM_Tomo_Only.py:89-148; kernels in pdhg.cu) ---------------------------------------
+extern "C" int admm_pdhg_dual(admm_plan* p, const float* d_xbar, long long stride, float* d_y1, float* d_y2,
+                              const float* d_q, const float* d_b, const float* d_sigma, float lam_data, float lam_tv,
+                              int node0, int nodes, void* stream) {
+    if (int e = check_nodes(p, node0, nodes)) return e;
+    if (!d_xbar || !d_y1 || !d_y2 || !d_q || !d_b || !d_sigma || lam_data <= 0.f || lam_tv <= 0.f)
+        return fail(ADMM_ERR_ARG, "admm_pdhg_dual: bad argument");
+    CK(launch_pdhg_dual(d_y1, d_y2, d_xbar, stride, d_q, d_b, p->d_anode, d_sigma, lam_data, lam_tv, p->N, p->D,
+                        p->aptr[node0], p->aptr[node0 + nodes], node0, nodes, (cudaStream_t)stream));
+    return ADMM_OK;
+}
+extern "C" int admm_pdhg_primal(admm_plan* p, float* d_x, float* d_xbar, long long stride, const float* d_back,
+                                const float* d_y2, const float* d_pull, const float* d_tau, const float* d_adj,
+                                float gamma, float theta, int node0, int nodes, void* stream) {
+    if (int e = check_nodes(p, node0, nodes)) return e;
+    if (!d_x || !d_xbar || !d_back || !d_y2 || !d_tau || !d_adj) return fail(ADMM_ERR_ARG, "admm_pdhg_primal: null buffer");
+    CK(launch_pdhg_primal(d_x, d_xbar, stride, d_back, d_y2, d_pull, d_tau, d_adj, gamma, theta, p->N, node0, nodes,
+                          (cudaStream_t)stream));
+    return ADMM_OK;
+}
+extern "C" int admm_pdhg_normal(admm_plan* p, const float* d_x, long long stride, const float* d_back, const float* d_adj,
+                                float* d_out, int node0, int nodes, void* stream) {
+    if (int e = check_nodes(p, node0, nodes)) return e;
+    if (!d_x || !d_back || !d_adj || !d_out) return fail(ADMM_ERR_ARG, "admm_pdhg_normal: null buffer");
+    CK(launch_pdhg_normal(d_out, d_x, stride, d_back, d_adj, p->N, node0, nodes, (cudaStream_t)stream));
+    return ADMM_OK;
+}
+extern "C" int admm_pdhg_combine(admm_plan* p, const float* d_x, long long stride, const float* d_colnorm,
+                                 const float* d_phantom, float* d_xa, int nodes, void* stream) {
+    if (int e = check_nodes(p, 0, nodes)) return e;
+    if (!d_x || !d_colnorm || !d_phantom || !d_xa) return fail(ADMM_ERR_ARG, "admm_pdhg_combine: null buffer");
+    CK(launch_pdhg_combine(d_xa, d_x, stride, d_colnorm, d_phantom, (long long)p->N * p->N, nodes, (cudaStream_t)stream));
+    return ADMM_OK;
+}
+extern "C" int admm_pdhg_sums(admm_plan* p, const float* d_x, long long stride, const float* d_phantom, const float* d_q,
+                              const float* d_b, double* d_out, int node0, int nodes, void* stream) {
+    if (int e = check_nodes(p, node0, nodes)) return e;
+    if (!d_x || !d_out) return fail(ADMM_ERR_ARG, "admm_pdhg_sums: null buffer");
+    CK(launch_pdhg_sums(d_out, d_x, stride, d_phantom, d_q, d_b, p->d_aptr, (long long)p->N * p->N, p->D, node0, nodes,
+                        (cudaStream_t)stream));
     return ADMM_OK;
 }
 

@@ -4,7 +4,9 @@
 // Replaces odl.tomo.RayTransform.__call__ / `Ai @ x` (block_2_load_odl_data.py:149,
 // block_6_admm_loop_ver2.py:145,193), `Ai.T @ r` (block_6_admm_loop_ver2.py:145) and
 // np.sum(A_i*A_i, axis=0) (block_3_graph_and_precisions.py:22).  Discretisation: SURVEY.md App. C.
+#include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 #include "projector.cuh"
 
@@ -20,13 +22,12 @@ namespace admm {
 // per slab -> no atomics).  At the end the rows are stored as fixed-size records; fwd_reduce_kernel sums
 // the records of all strips/segments in a fixed order (deterministic) and applies the step weight.
 // =================================================================================================
-constexpr bool kPrefetchNextSlab = false;
-
 __global__ void __launch_bounds__(FTHREADS, 4)
-fwd_strip_kernel(const FwdParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* S = reinterpret_cast<float*>(smem_raw);                 // [FL][FPITCH]
-    float* acc_s = S + FL * FPITCH;                                // [FAC][span]
+fwd_strip_kernel(const __grid_constant__ FwdParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* S = reinterpret_cast<float*>(smem_raw);                 // [FL][FPITCH]  ([FL][FPITCH_T] when landed by TMA)
+    float* acc_s = S + FL * FPITCH_T;                              // [FAC][span]
+    __shared__ __align__(8) unsigned long long s_bar;              // TMA arrival barrier of the tile copy
     double* s_base = reinterpret_cast<double*>(acc_s + FAC * P.span + ((FAC * P.span) & 1));  // [FAC]
     int* s_jseg = reinterpret_cast<int*>(s_base + FAC);            // [FAC]
     int* s_aid = s_jseg + FAC;                                     // [FAC]
@@ -44,6 +45,14 @@ fwd_strip_kernel(const FwdParams P) {
     if (a0 >= oend) return;
     const int na = min(FAC, oend - a0);
     const bool xdom = (orient == 0);
+    // y-dominant tiles of a plain projection land by ONE bulk tensor copy per slab (pitch FPITCH_T, zero-filled outside
+    // the image); everything else is staged by the threads (pitch FPITCH, transposed / CG-updated on the way in)
+    const bool ytma = !xdom && P.mode == 0 && (P.use_tma & 2);
+    unsigned bar_phase = 0;
+    if (ytma && threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+    }
 
     const float* __restrict__ img = P.img + (long long)blockIdx.y * P.img_stride;
     const int U0 = ti * FW, Wt = min(FW, N - U0);
@@ -150,7 +159,7 @@ fwd_strip_kernel(const FwdParams P) {
     const int slot = tid / FTPA, t = tid % FTPA;
     const int nslab = (Kseg + FL - 1) / FL;
     // shared-window byte address of S[0][-1+1] minus the magic-number bias: addr(k, i) = sbase + k*pitch*4 + bits(i)*4
-    const unsigned sbase = smem_u32(S) + 4u * FHALO - ((unsigned)kMagicBits << 2);
+    const unsigned sbase = smem_u32(S) + 4u * (ytma ? FHALO_T : FHALO) - ((unsigned)kMagicBits << 2);
     for (int slab = 0; slab < nslab; ++slab) {
         const int K0 = K0seg + slab * FL, Lt = min(FL, K0seg + Kseg - K0);
         __syncthreads();  // previous slab fully consumed (also orders the acc/zero + setup writes)
@@ -164,11 +173,17 @@ fwd_strip_kernel(const FwdParams P) {
             s_win[tid] = make_int4(max(0, (int)ceil(tlo)), min(D - 1, (int)floor(thi)), (int)fbase,
                                    __float_as_int((float)(base - fbase)));
         }
+        if (ytma && tid == 0) {
+            // the previous slab's reads (and this thread's halo stores) are ordered before the copy unit's writes
+            fence_proxy_async();
+            mbar_expect_tx(&s_bar, (unsigned)(FL * FPITCH_T * sizeof(float)));
+            tma_load_3d(S, &P.mapY[0], U0 - FHALO_T, K0, (int)blockIdx.y, &s_bar);
+        }
         // ---- stage tile -------------------------------------------------------------------------
         // x-dominant: pixel (ix = U0+u, iy = K0+k) is contiguous along the step axis k -> item = (u, 4 consecutive k),
         //             stored transposed (stride FPITCH, odd -> conflict-free up to 2-way);
         // y-dominant: pixel (ix = K0+k, iy = U0+u) is contiguous along the interpolation axis u -> item = (k, 4 u).
-        {
+        if (!ytma) {
             const int per_row = xdom ? (FL / 4) : (FW / 4);            // float4 items per contiguous run
             const int nitems = xdom ? FW * (FL / 4) : FL * (FW / 4);
             auto decode = [&](int idx, int& row, int& c4, bool& full, bool& any, long long& g) {
@@ -208,40 +223,43 @@ fwd_strip_kernel(const FwdParams P) {
                 store(rowA, cA, va);
             }
         }
-        for (int k = tid; k < FL; k += FTHREADS) {
-            S[k * FPITCH] = 0.f;
-            S[k * FPITCH + 1] = 0.f;
-            S[k * FPITCH + FW + 2] = 0.f;
-            S[k * FPITCH + FW + 3] = 0.f;
-            S[k * FPITCH + FW + 4] = 0.f;
-        }
-        __syncthreads();
-        // ---- pull the next slab's operands towards L2 while this slab is sampled (staging is latency-bound) ----
-        if (kPrefetchNextSlab && slab + 1 < nslab) {
-            const int K1 = K0 + FL;
-            if (xdom) {
-                for (int idx = tid; idx < FW * (FL / 32); idx += FTHREADS) {   // one 128-byte line per request
-                    const int u = idx / (FL / 32), kk = (idx % (FL / 32)) * 32;
-                    if (u < Wt && K1 + kk < N) {
-                        const long long g = (long long)(U0 + u) * N + K1 + kk;
-                        prefetch_l2(img + g);
-                        if (mode != 0) prefetch_l2(rimg + g);
-                        if (mode == 2) { prefetch_l2(hpimg + g); if (writer) prefetch_l2(xio + g); }
-                    }
-                }
-            } else {
-                for (int idx = tid; idx < FL * ((FW + 31) / 32); idx += FTHREADS) {
-                    const int k = idx / ((FW + 31) / 32), uu = (idx % ((FW + 31) / 32)) * 32;
-                    if (K1 + k < N && uu < Wt) {
-                        const long long g = (long long)(K1 + k) * N + U0 + uu;
-                        prefetch_l2(img + g);
-                        if (mode != 0) prefetch_l2(rimg + g);
-                        if (mode == 2) { prefetch_l2(hpimg + g); if (writer) prefetch_l2(xio + g); }
-                    }
-                }
+        if (ytma) {
+            // the box brought the neighbouring strips' pixels into the halo columns: a tile contributes only what it owns
+            mbar_wait(&s_bar, bar_phase);
+            bar_phase ^= 1;
+            for (int k = tid; k < FL; k += FTHREADS) {
+                S[k * FPITCH_T + FHALO_T - 2] = 0.f;
+                S[k * FPITCH_T + FHALO_T - 1] = 0.f;
+                S[k * FPITCH_T + FHALO_T + FW] = 0.f;
+                S[k * FPITCH_T + FHALO_T + FW + 1] = 0.f;
+                S[k * FPITCH_T + FHALO_T + FW + 2] = 0.f;
+            }
+        } else {
+            for (int k = tid; k < FL; k += FTHREADS) {
+                S[k * FPITCH] = 0.f;
+                S[k * FPITCH + 1] = 0.f;
+                S[k * FPITCH + FW + 2] = 0.f;
+                S[k * FPITCH + FW + 3] = 0.f;
+                S[k * FPITCH + FW + 4] = 0.f;
             }
         }
-        // ---- sample ---------------------------------------------------------------------------------
+        __syncthreads();
+        // ---- pull the next slab's operand boxes towards L2 while this slab is sampled: one instruction per stream ----
+        if ((P.use_tma & 1) && tid == 32 && slab + 1 < nslab) {
+            const int K1 = K0 + FL, nd = (int)blockIdx.y;
+            if (xdom) {
+                tma_prefetch_3d(&P.mapX[0], K1, U0, nd);
+                if (mode != 0) tma_prefetch_3d(&P.mapX[1], K1, U0, nd);
+                if (mode == 2) { tma_prefetch_3d(&P.mapX[2], K1, U0, nd); if (writer) tma_prefetch_3d(&P.mapX[3], K1, U0, nd); }
+            } else {
+                tma_prefetch_3d(&P.mapY[0], U0, K1, nd);
+                if (mode != 0) tma_prefetch_3d(&P.mapY[1], U0, K1, nd);
+                if (mode == 2) { tma_prefetch_3d(&P.mapY[2], U0, K1, nd); if (writer) tma_prefetch_3d(&P.mapY[3], U0, K1, nd); }
+            }
+        }
+        // ---- sample (instantiated for the two row pitches: the row offsets are immediates) -----------------
+        auto sample = [&](auto pitch_c) {
+        constexpr int PITCH = decltype(pitch_c)::value;
         for (int ai = slot; ai < na; ai += FTHREADS / FTPA) {
             const int4 win = s_win[ai];
             const float4 ar = s_ang[ai];
@@ -266,7 +284,7 @@ fwd_strip_kernel(const FwdParams P) {
                 f32x2 acc2 = splat2(0.f);      // packed partial sums of the (even, odd) steps of the 8-step blocks
                 const f32x2 s2 = splat2(s);
                 float kf = (float)klo;
-                unsigned rowa = sbase + (unsigned)(klo * FPITCH * 4);
+                unsigned rowa = sbase + (unsigned)(klo * PITCH * 4);
                 int k = klo;
                 // one sample: fi = floor(u) + magic (exact, FADD.RM), f = u - floor(u), both taps through one address
                 // register, acc += a + f (b - a).  The 8-step block does two steps per instruction with the packed fp32
@@ -291,19 +309,19 @@ fwd_strip_kernel(const FwdParams P) {
                         float fia, fib;
                         unpack2(fi, fia, fib);
                         float a0, b0, a1, b1;
-                        lds_pair((__float_as_uint(fia) << 2) + rowa + (unsigned)(q * FPITCH * 4), a0, b0);
-                        lds_pair((__float_as_uint(fib) << 2) + rowa + (unsigned)((q + 1) * FPITCH * 4), a1, b1);
+                        lds_pair((__float_as_uint(fia) << 2) + rowa + (unsigned)(q * PITCH * 4), a0, b0);
+                        lds_pair((__float_as_uint(fib) << 2) + rowa + (unsigned)((q + 1) * PITCH * 4), a1, b1);
                         const f32x2 av = pack2(a0, a1);
                         acc2 = add2(acc2, fma2(f, sub2(pack2(b0, b1), av), av));
                     }
                     kf += 8.f;
-                    rowa += 8 * FPITCH * 4;
+                    rowa += 8 * PITCH * 4;
                 }
                 for (; k <= khi; ++k) {
                     const float u = fmaf(-kf, s, u0);
                     FWD_SAMPLE(u, 0u)
                     kf += 1.f;
-                    rowa += FPITCH * 4;
+                    rowa += PITCH * 4;
                 }
 #undef FWD_SAMPLE
                 {
@@ -315,6 +333,9 @@ fwd_strip_kernel(const FwdParams P) {
                 if (idx >= 0 && idx < span) acc_s[ai * span + idx] += acc;
             }
         }
+        };
+        if (ytma) sample(std::integral_constant<int, FPITCH_T>{});
+        else sample(std::integral_constant<int, FPITCH>{});
     }
     __syncthreads();
     const int nRec = nTi * nSeg, rec = sg * nTi + ti;
@@ -356,18 +377,27 @@ fwd_reduce_kernel(const FwdReduceParams P) {
 // =================================================================================================
 template <int MODE>
 __global__ void __launch_bounds__(BTHREADS)
-back_tile_kernel(const BackParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* qs = reinterpret_cast<float*>(smem_raw);       // [BAC][bspan]
-    float4* s_c = reinterpret_cast<float4*>(qs + BAC * P.bspan + ((4 - ((BAC * P.bspan) & 3)) & 3));  // [BAC]
+back_tile_kernel(const __grid_constant__ BackParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* qs = reinterpret_cast<float*>(smem_raw);       // [BAC][bpitch]  (every window 128-byte aligned with TMA)
+    float4* s_c = reinterpret_cast<float4*>(qs + BAC * P.bpitch + ((4 - ((BAC * P.bpitch) & 3)) & 3));  // [BAC]
     unsigned* s_qa = reinterpret_cast<unsigned*>(s_c + BAC);  // [BAC] biased shared-window address of each window
     int* s_jw = reinterpret_cast<int*>(s_qa + BAC);           // [BAC] first detector bin of each window
     float* s_sc = reinterpret_cast<float*>(s_jw + BAC);       // [BAC] window scale (step weight * precision)
     __shared__ __align__(16) float red[96];
+    __shared__ __align__(8) unsigned long long s_bar;         // TMA arrival barrier of the window copies
 
     const int node = P.node0 + blockIdx.z;
     if (P.ctl && !P.ctl[node].active) return;   // a14 retry pass: this node was accepted already
-    const int N = P.N, D = P.D, bspan = P.bspan;
+    const int N = P.N, D = P.D, bspan = P.bpitch;   // row pitch of the staged windows
+    // TMA staging: raw sinogram windows land by bulk tensor copies (zero-filled outside [0, D)); the window scale is
+    // folded into the hat weights instead of the staged values
+    const bool tma = (MODE != BACK_COLNORM2) && P.use_tma;
+    unsigned bar_phase = 0;
+    if (tma && threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+    }
     const int X0 = blockIdx.y * BTX, Y0 = blockIdx.x * BTY;
     const int tid = threadIdx.x;
     const int lx = tid >> 3, ly = (tid & 7) * 4;          // pixels (X0+lx, Y0+32*g+ly+{0..3}), g < BPG
@@ -392,7 +422,8 @@ back_tile_kernel(const BackParams P) {
             const double tau0 = cj + (X0 - cx) * r.ct + (Y0 - cx) * r.st;  // tau of tile pixel (0,0)
             const double e1 = (BTX - 1) * r.ct, e2 = (BTY - 1) * r.st;
             const double om = (double)(1.0f / r.inv_om);
-            const int jw0 = (int)floor(tau0 + fmin(e1, 0.0) + fmin(e2, 0.0) - om) - 1;
+            int jw0 = (int)floor(tau0 + fmin(e1, 0.0) + fmin(e2, 0.0) - om) - 1;
+            if (tma) jw0 &= ~3;   // a box must start on a 16-byte boundary of the sinogram row (bpitch has the slack)
             // window-relative tau of pixel (0,0), pre-biased by -1/2 for the rint trick
             s_c[tid] = make_float4((float)(tau0 - (double)jw0 - 0.5), (float)r.ct, (float)r.st, r.inv_om);
             // read back through shared memory so the magic-number bias stays folded into ONE register
@@ -400,31 +431,45 @@ back_tile_kernel(const BackParams P) {
             s_jw[tid] = jw0;
             s_sc[tid] = (MODE == BACK_COLNORM2) ? r.wgt * r.wgt : r.wgt * prec;
         }
-        __syncthreads();
-        // stage the detector windows: one warp per angle row, coalesced
-        for (int ai = tid >> 5; ai < na; ai += BTHREADS / 32) {
-            const int jw0 = s_jw[ai];
-            const float sc = s_sc[ai];
-            const float* __restrict__ qrow = P.q + (long long)(c0 + ai) * D;
-            for (int k = (tid & 31); k < bspan; k += 32) {
-                const int j = jw0 + k;
-                float val = 0.f;
-                if (j >= 0 && j < D) val = (MODE == BACK_COLNORM2) ? sc : sc * qrow[j];
-                qs[ai * bspan + k] = val;
+        if (tma) {
+            // the threads that computed the windows (all in warp 0) issue one box copy each; lane 0 arms the barrier
+            // with the total byte count first
+            if (tid < 32) {
+                if (tid == 0) mbar_expect_tx(&s_bar, (unsigned)(na * bspan * 4));
+                __syncwarp();
+                if (tid < na) tma_load_2d(qs + tid * bspan, &P.qmap, s_jw[tid], c0 + tid, &s_bar);
             }
+            __syncthreads();                 // window records visible to every thread
+            mbar_wait(&s_bar, bar_phase);    // window data has landed
+            bar_phase ^= 1;
+        } else {
+            __syncthreads();
+            // stage the detector windows: one warp per angle row, coalesced
+            for (int ai = tid >> 5; ai < na; ai += BTHREADS / 32) {
+                const int jw0 = s_jw[ai];
+                const float sc = s_sc[ai];
+                const float* __restrict__ qrow = P.q + (long long)(c0 + ai) * D;
+                for (int k = (tid & 31); k < bspan; k += 32) {
+                    const int j = jw0 + k;
+                    float val = 0.f;
+                    if (j >= 0 && j < D) val = (MODE == BACK_COLNORM2) ? sc : sc * qrow[j];
+                    qs[ai * bspan + k] = val;
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
         for (int ai = 0; ai < na; ++ai) {
             const float4 c = s_c[ai];
             const float a = c.w;  // 1/omega
             const float tb = fmaf(fx, c.y, fmaf(fy, c.z, c.x));   // tau - 1/2 of this thread's first pixel
+            const float wsc = tma ? s_sc[ai] : 1.f;               // TMA: raw windows, the scale rides on the weights
             if (a >= 1.0f) {
                 // omega <= 1 bin: the hat touches bins rint(tau - 1/2) and the next one.  Pixel pairs (iy, iy+1) go
                 // through the packed fp32 pipe: per pair 1 FFMA2 (tau) + 3 FADD2 (rint, fraction) + 2 FFMA2 (weights)
                 // + 2 FFMA2 (accumulate) next to the per-pixel LEA / 2 LDS / 2 FMNMX.
-                const float c1 = fmaf(-0.5f, a, 1.f);
+                const float c1 = fmaf(-0.5f, a, 1.f) * wsc, as = a * wsc;
                 const unsigned qa = s_qa[ai];
-                const f32x2 tb2 = pack2(tb, tb + c.z), cz2 = splat2(c.z), a2 = splat2(a), na2 = splat2(-a), c12 = splat2(c1);
+                const f32x2 tb2 = pack2(tb, tb + c.z), cz2 = splat2(c.z), a2 = splat2(as), na2 = splat2(-as), c12 = splat2(c1);
 #pragma unroll
                 for (int k = 0; k < 2 * BPG; ++k) {
                     const float o = (float)(2 * (k & 1) + 32 * (k >> 1));   // iy offset of the pair's first pixel
@@ -456,7 +501,7 @@ back_tile_kernel(const BackParams P) {
                         const float tau = fmaf(off, c.z, tb) + 0.5f;
                         const int jlo = (int)ceilf(tau - om), jhi = (int)floorf(tau + om);
                         for (int j = max(jlo, 0); j <= min(jhi, bspan - 1); ++j) {
-                            float w = fmaxf(0.f, 1.f - fabsf(tau - (float)j) * a);
+                            float w = fmaxf(0.f, 1.f - fabsf(tau - (float)j) * a) * wsc;
                             if (MODE == BACK_COLNORM2) w *= w;
                             ap[e] = fmaf(w, qa[j], ap[e]);
                         }
@@ -586,13 +631,38 @@ back_tile_kernel(const BackParams P) {
 
 // ---- host launchers ---------------------------------------------------------------------------------
 static size_t fwd_smem_bytes(int span) {
-    size_t f = (size_t)FL * FPITCH + (size_t)FAC * span;
+    size_t f = (size_t)FL * FPITCH_T + (size_t)FAC * span;
     f += (f & 1);
     return f * sizeof(float) + FAC * sizeof(double) + 2 * FAC * sizeof(int) + FAC * sizeof(int4) + FAC * sizeof(float4);
 }
 
-cudaError_t launch_forward(const FwdParams& P, int nodes, int max_chunks, const FwdReduceParams& R,
+// ADMM_B200_TMA = bit mask of the TMA uses that are on (default 7): 1 back-projector windows, 2 forward L2 prefetch of
+// the next slab, 4 forward y-dominant tile landing.  The staging-loop paths stay selectable for A/B measurements.
+static int tma_mask() {
+    static const int m = [] { const char* e = getenv("ADMM_B200_TMA"); return e ? atoi(e) : 7; }();
+    return m;
+}
+
+// tensor maps of one operand stream [nodes][N][N] (node stride `stride` floats)
+static bool fwd_maps(const float* base, int N, long long stride, int nodes, CUtensorMap* mapY, CUtensorMap* mapX) {
+    const unsigned long long dims[3] = {(unsigned long long)N, (unsigned long long)N, (unsigned long long)nodes};
+    const unsigned long long strides[2] = {(unsigned long long)N * sizeof(float), (unsigned long long)stride * sizeof(float)};
+    const unsigned boxY[3] = {(unsigned)FPITCH_T, (unsigned)FL, 1u}, boxX[3] = {(unsigned)FL, (unsigned)FW, 1u};
+    return tma_encode_f32(mapY, base, 3, dims, strides, boxY) && tma_encode_f32(mapX, base, 3, dims, strides, boxX);
+}
+
+cudaError_t launch_forward(const FwdParams& P0, int nodes, int max_chunks, const FwdReduceParams& R,
                            cudaStream_t st) {
+    FwdParams P = P0;
+    P.use_tma = 0;
+    if (tma_mask() & 6) {
+        bool ok = fwd_maps(P.img, P.N, P.img_stride, nodes, &P.mapY[0], &P.mapX[0]);
+        if (ok && P.mode != 0) ok = fwd_maps(P.r, P.N, P.img_stride, nodes, &P.mapY[1], &P.mapX[1]);
+        if (ok && P.mode == 2)
+            ok = fwd_maps(P.hp, P.N, P.img_stride, nodes, &P.mapY[2], &P.mapX[2]) &&
+                 fwd_maps(P.x_io, P.N, P.img_stride, nodes, &P.mapY[3], &P.mapX[3]);
+        if (ok) P.use_tma = ((tma_mask() & 2) ? 1 : 0) | ((tma_mask() & 4) ? 2 : 0);
+    }
     // the dynamic shared-memory limit is a per-device function attribute: remember what was set on EACH device
     static std::mutex mu;
     static int configured_span[64];
@@ -618,8 +688,23 @@ cudaError_t launch_forward(const FwdParams& P, int nodes, int max_chunks, const 
     return cudaGetLastError();
 }
 
-cudaError_t launch_back(int mode, const BackParams& P, int nodes, cudaStream_t st) {
-    size_t f = (size_t)BAC * P.bspan;
+cudaError_t launch_back(int mode, const BackParams& P0, int nodes, cudaStream_t st) {
+    BackParams P = P0;
+    P.bpitch = P.bspan;
+    P.use_tma = 0;
+    if (mode != BACK_COLNORM2 && (tma_mask() & 1) && P.q) {
+        // sinogram rows as a 2-D tensor [rows >= every angle row of this launch][D]; a window is the box (bpitch, 1)
+        // at (jw0, row).  The row count only bounds the coordinates: one past the last angle row the kernel can touch
+        const unsigned bp = (unsigned)((P.bspan + 3 + 31) & ~31);   // + 3: the window origin is rounded down to a multiple of 4 bins
+        const unsigned long long dims[2] = {(unsigned long long)P.D, (unsigned long long)P.A_rows};
+        const unsigned long long strides[1] = {(unsigned long long)P.D * sizeof(float)};
+        const unsigned box[2] = {bp, 1u};
+        if (bp <= 256 && P.A_rows > 0 && tma_encode_f32(&P.qmap, P.q, 2, dims, strides, box)) {
+            P.bpitch = (int)bp;
+            P.use_tma = 1;
+        }
+    }
+    size_t f = (size_t)BAC * P.bpitch;
     f += (4 - (f & 3)) & 3;
     const size_t smem = f * sizeof(float) + BAC * sizeof(float4) + BAC * (sizeof(unsigned) + sizeof(int) + sizeof(float));
     dim3 grid((P.N + BTY - 1) / BTY, (P.N + BTX - 1) / BTX, nodes);

@@ -1,6 +1,7 @@
 // projector.cuh -- launch parameter blocks of the Joseph projector kernels (K1, K2, K2b).
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace admm {
 
@@ -13,6 +14,9 @@ constexpr int FAC = 16;       // angles per block chunk
 constexpr int FTHREADS = 256; // 2 angle slots
 constexpr int FPITCH = FW + 5;  // smem row pitch (odd): [2 zero columns][0..FW)[3 zero columns]
 constexpr int FHALO = 2;        // leading zero columns
+constexpr int FPITCH_T = 116;   // row pitch of a y-dominant tile landed by TMA: the box (FPITCH_T, FL) at column U0 - FHALO_T
+constexpr int FHALO_T = 4;      // leading columns of that tile: a box must start on a 16-byte boundary of the image row
+static_assert(FW % 4 == 0 && FHALO_T % 4 == 0 && FHALO_T + FW + 3 <= FPITCH_T, "TMA tile layout");
 
 struct FwdParams {
     const float* img;        // [nodes][N*N] images to project (p or x)
@@ -41,6 +45,12 @@ struct FwdParams {
     unsigned* counter;       // [nodes]
     int rr_out;              // mode 2: slot receiving <r', r'>
     const NodeCtl* ctl;      // masked launches (a14 retry passes): blocks of nodes with ctl[node].active == 0 exit
+    // TMA (tma.cuh).  Operand streams as 3-D tensors [nodes][N][N]: 0 img, 1 r, 2 hp, 3 x.  mapY: box (FPITCH_T, FL, 1)
+    // = a y-dominant slab tile incl. halo columns; mapX: box (FL, FW, 1) = an x-dominant slab tile.
+    // use_tma bit 0: the next slab's boxes are prefetched to L2 while the current slab is sampled;
+    //         bit 1: mode-0 y-dominant tiles land in shared memory by cp.async.bulk.tensor (no staging loop).
+    int use_tma;
+    CUtensorMap mapY[4], mapX[4];
 };
 
 struct FwdReduceParams {
@@ -90,6 +100,11 @@ struct BackParams {
     double* scal;            // [V][NSCAL]
     int dot_slot;
     const NodeCtl* ctl;      // masked launches: skip inactive nodes (nullptr: all nodes)
+    // detector windows by TMA (tma.cuh): q as a 2-D tensor [A][D], box = (bpitch, 1); use_tma = 0 keeps the staging loop
+    int A_rows;              // angle rows behind q (set by the plan; bounds the tensor map)
+    int bpitch;              // shared-memory row pitch of a window (bspan, or bspan rounded up to 32 floats with TMA)
+    int use_tma;
+    CUtensorMap qmap;
 };
 
 constexpr int NSCAL = 16;  // doubles per node in the scalar table

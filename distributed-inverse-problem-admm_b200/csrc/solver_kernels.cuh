@@ -128,5 +128,18 @@ cudaError_t launch_dense_back(const float* A, int mode, const BackParams& P, int
 cudaError_t launch_rs_forward(const float2* cs, const int* anode, double det_w, const FwdParams& P, int nodes,
                               const FwdReduceParams& R, cudaStream_t st);
 cudaError_t launch_rs_back(const float2* cs, double det_w, int mode, const BackParams& P, int nodes, cudaStream_t st);
+// PDHG consensus variant (pdhg.cu): element-wise / stencil pieces of one PDHG step, batched over nodes
+cudaError_t launch_pdhg_dual(float* y1, float* y2, const float* xbar, long long stride, const float* q, const float* b,
+                             const int* anode, const float* sigma, float lam_d, float lam_t, int N, int D, int A0, int A1,
+                             int node0, int nodes, cudaStream_t st);
+cudaError_t launch_pdhg_primal(float* x, float* xbar, long long stride, const float* back, const float* y2,
+                               const float* pull, const float* tau, const float* adj, float gamma, float theta, int N,
+                               int node0, int nodes, cudaStream_t st);
+cudaError_t launch_pdhg_normal(float* out, const float* x, long long stride, const float* back, const float* adj, int N,
+                               int node0, int nodes, cudaStream_t st);
+cudaError_t launch_pdhg_combine(float* xa, const float* x, long long stride, const float* cn, const float* phantom,
+                                long long n, int nodes, cudaStream_t st);
+cudaError_t launch_pdhg_sums(double* out, const float* x, long long stride, const float* phantom, const float* q,
+                             const float* b, const int* aptr, long long n, int D, int node0, int nodes, cudaStream_t st);
 
 }  // namespace admm

@@ -237,6 +237,31 @@ int admm_kt_subgrad_host(int N, const double* h_x, double eps, int exact_adjoint
 int admm_pixel_masks(int V, long long n, int strategy, int k, int harmonic, const float* d_W,
                      const unsigned char* d_perm, unsigned* d_keep_bits, void* stream);
 
+/* ---- PDHG consensus variant   ADMM_Tomo_Only.py:89-148 ------------------------------------------------
+ * The element-wise / stencil pieces of odl.solvers.pdhg (:132-133, :148) for
+ *   min_x gamma |x - x_a|^2 + lam_data |A_i x - b_i|^2 + lam_tv |G x|_{2,1},   L = (A_i, G), batched over nodes;
+ * A xbar and A^T y1 are admm_forward / admm_adjoint calls.  All buffers are DEVICE fp32; d_sigma, d_tau, d_adj are [V]
+ * per-node step sizes and the adjoint factor w_Y / w_X (A* = adj * A^T).  G = forward differences / h, zero padding.
+ * admm_pdhg_dual   : y1 <- (y1 + sigma (q - b)) / (1 + sigma / (2 lam_data)),  q = A xbar  ([A][D], global angle rows);
+ *                    y2 <- proj_{|.|_2 <= lam_tv}(y2 + sigma G xbar)                         ([V][2][n])
+ * admm_pdhg_primal : x <- (x - tau (adj * back + G^T y2) + 2 tau gamma pull) / (1 + 2 tau gamma), back = A^T y1;
+ *                    xbar <- x' + theta (x' - x);  d_pull = the shared n-vector x_a (:117-118) or NULL (f = 0, :142)
+ * admm_pdhg_normal : out = adj * back + G^T G x, back = A^T (A x): one step of power_method_opnorm (:128, :145)
+ * admm_pdhg_combine: x_a = sum_i eta_i x_i / (sum_i eta_i + 1e-8), eta_i = colnorm_i / (|x_i - phantom| + 1e-8) (:100-118)
+ * admm_pdhg_sums   : d_out[node][2] (fp64) = { sum (x - phantom)^2 (sum x^2 if phantom NULL), sum (q - b)^2 over the
+ *                    node's sinogram rows (0 if q NULL; b NULL: sum q^2) }                    (:134-139 metrics, norms) */
+int admm_pdhg_dual(admm_plan* plan, const float* d_xbar, long long stride, float* d_y1, float* d_y2, const float* d_q,
+                   const float* d_b, const float* d_sigma, float lam_data, float lam_tv, int node0, int nodes, void* stream);
+int admm_pdhg_primal(admm_plan* plan, float* d_x, float* d_xbar, long long stride, const float* d_back, const float* d_y2,
+                     const float* d_pull, const float* d_tau, const float* d_adj, float gamma, float theta, int node0,
+                     int nodes, void* stream);
+int admm_pdhg_normal(admm_plan* plan, const float* d_x, long long stride, const float* d_back, const float* d_adj,
+                     float* d_out, int node0, int nodes, void* stream);
+int admm_pdhg_combine(admm_plan* plan, const float* d_x, long long stride, const float* d_colnorm, const float* d_phantom,
+                      float* d_xa, int nodes, void* stream);
+int admm_pdhg_sums(admm_plan* plan, const float* d_x, long long stride, const float* d_phantom, const float* d_q,
+                   const float* d_b, double* d_out, int node0, int nodes, void* stream);
+
 /* launches issued by this library since load (the bench's gpu_launches evidence) */
 long long admm_launch_count(void);
 

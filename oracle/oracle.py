@@ -678,3 +678,116 @@ def decentralized_admm(ops, sinograms, G, Wi_list, Qij_diag_fn, N, lam_tv=0.01, 
         if stop and pri_norm < eps_pri and dual_norm < eps_dual:
             break
     return x, hist
+
+
+# ---- PDHG consensus variant (ADMM_Tomo_Only.py:89-148) -- NumPy fp64 restatement -----------------
+# Test infrastructure like the rest of this file.  PARITY UNPINNED at odl.solvers.pdhg / odl.Gradient /
+# odl.power_method_opnorm (ODL is not installable here and the reference holds no vectors for this script): the
+# conventions below are ODL's as recalled and are stated, not verified -- X = uniform_discr([-1,1]^2, (N,N)), cell
+# h = 2/N; Gradient = forward differences / h with zero padding beyond the last index; adjoint of the ray transform
+# = (w_Y / w_X) A^T; prox formulas of L2NormSquared.translated and GroupL1Norm (weights cancel in both).
+def odl_grad(x, N):
+    """odl.Gradient(space)(x): forward differences / h, zero padding (ADMM_Tomo_Only.py:63)."""
+    X = x.reshape(N, N)
+    ih = N / 2.0
+    g1 = np.vstack([X[1:], np.zeros((1, N))]) - X
+    g2 = np.hstack([X[:, 1:], np.zeros((N, 1))]) - X
+    return g1 * ih, g2 * ih
+
+
+def odl_grad_adjoint(p1, p2, N):
+    """Gradient.adjoint (= -Divergence with the matching zero padding): the plain transpose of odl_grad."""
+    ih = N / 2.0
+    a = np.vstack([np.zeros((1, N)), p1[:-1]]) - p1
+    b = np.hstack([np.zeros((N, 1)), p2[:, :-1]]) - p2
+    return ((a + b) * ih).reshape(-1)
+
+
+def pdhg_opnorm(op, adj_scale, N, iters=30):
+    """odl.power_method_opnorm(BroadcastOperator(A, Gradient)) (:128,:145) from a deterministic start (the reference's
+    is random): `iters` steps of x <- L* L x / |.|, returns sqrt(|L* L x| / |x|) of the last step."""
+    n = N * N
+    x = 1.0 + 0.5 * np.cos(0.37 * np.arange(n))
+    est = 0.0
+    for _ in range(iters):
+        x = x / np.linalg.norm(x)
+        g1, g2 = odl_grad(x, N)
+        y = adj_scale * op.adjoint(op.forward(x)) + odl_grad_adjoint(g1, g2, N)
+        est = math.sqrt(np.linalg.norm(y))
+        x = y
+    return est
+
+
+def pdhg_steps(op, adj_scale, b, x, y1, y2, niter, tau, sigma, gamma, pull, lam_d, lam_t, N, theta=1.0):
+    """`niter` steps of odl.solvers.pdhg (:132-133) for gamma|x - pull|^2 + lam_d|A x - b|^2 + lam_t|G x|_{2,1};
+    x_relax starts at x (pdhg's default).  `op` may be a list (aggregate problem: rows stacked, `b`, `y1` lists)."""
+    ops = op if isinstance(op, (list, tuple)) else [op]
+    bs = b if isinstance(b, (list, tuple)) else [b]
+    y1s = y1 if isinstance(y1, (list, tuple)) else [y1]
+    sc = adj_scale if isinstance(adj_scale, (list, tuple)) else [adj_scale] * len(ops)
+    xbar = x.copy()
+    for _ in range(niter):
+        for k, o in enumerate(ops):
+            y1s[k] = (y1s[k] + sigma * (o.forward(xbar) - bs[k])) / (1.0 + sigma / (2.0 * lam_d))
+        g1, g2 = odl_grad(xbar, N)
+        t1, t2 = y2[0] + sigma * g1, y2[1] + sigma * g2
+        s = np.maximum(1.0, np.sqrt(t1 * t1 + t2 * t2) / lam_t)
+        y2 = (t1 / s, t2 / s)
+        back = sum(sc[k] * o.adjoint(y1s[k]) for k, o in enumerate(ops))
+        v = x - tau * (back + odl_grad_adjoint(y2[0], y2[1], N))
+        w = 2.0 * tau * gamma
+        xn = (v + (w * pull if pull is not None else 0.0)) / (1.0 + w)
+        xbar = xn + theta * (xn - x)
+        x = xn
+    return x, (y1s if isinstance(y1, (list, tuple)) else y1s[0]), y2
+
+
+def pdhg_consensus(ops, sinograms, phantom, N, niter=100, lambda_penalty=0.005, alpha_tv=0.0, lambda_agg=0.005,
+                   gamma=2.0, node_niter=5, agg_niter=15, opnorm_iters=30, angle_cells=None, agg_angle_cell=None):
+    """ADMM_Tomo_Only.py:89-148: per outer iteration the error-weighted convex combination x_a of the node iterates
+    (:100-118, ground-truth dependent), 5 cold-dual PDHG steps per node pulled towards x_a (:121-133), 15 warm-dual PDHG
+    steps of the aggregate problem (:142-148), and the four metric lists (:134-139, :152-159)."""
+    V, n = len(ops), N * N
+    ph = np.asarray(phantom, dtype=np.float64).reshape(-1)
+    b = [np.asarray(s, dtype=np.float64).reshape(-1) for s in sinograms]
+    hx2 = (2.0 / N) ** 2
+    cells = [math.pi / o.nang for o in ops] if angle_cells is None else list(angle_cells)
+    adj = [c * (o.det_w / o.D) / hx2 for c, o in zip(cells, ops)]
+    agg_cell = (math.pi / sum(o.nang for o in ops)) if agg_angle_cell is None else agg_angle_cell
+    adj_agg = [agg_cell * (o.det_w / o.D) / hx2 for o in ops]
+    cn = [np.sqrt(o.colnorm2()) for o in ops]                            # :55 np.linalg.norm(A_i, axis=0)
+    norms = [pdhg_opnorm(o, a, N, opnorm_iters) for o, a in zip(ops, adj)]
+
+    class _Agg:   # the stacked operator with the aggregate range weighting
+        def forward(self, x): return np.concatenate([o.forward(x) for o in ops])
+        def adjoint(self, q):
+            out, pos = np.zeros(n), 0
+            for o in ops:
+                out += o.adjoint(q[pos:pos + o.shape[0]])
+                pos += o.shape[0]
+            return out
+    norm_agg = pdhg_opnorm(_Agg(), adj_agg[0], N, opnorm_iters)
+    x = [np.zeros(n) for _ in range(V)]
+    x_agg = np.zeros(n)
+    y1_agg = [np.zeros_like(bi) for bi in b]
+    y2_agg = (np.zeros((N, N)), np.zeros((N, N)))
+    out = {"mse_lists": [[] for _ in range(V)], "mse_sino_lists": [[] for _ in range(V)], "mse_agg_list": [],
+           "mse_agg_sino_list": [], "op_norms": norms, "op_norm_agg": norm_agg}
+    for k in range(niter):
+        lam = lambda_penalty * math.exp(alpha_tv * k)
+        eta = np.stack([cn[i] / (np.abs(x[i] - ph) + 1e-8) for i in range(V)])
+        xa = np.sum((eta / (eta.sum(axis=0) + 1e-8)) * np.stack(x), axis=0)
+        for i in range(V):
+            t = 1.0 / norms[i]
+            x[i], _, _ = pdhg_steps(ops[i], adj[i], b[i], x[i], np.zeros_like(b[i]),
+                                    (np.zeros((N, N)), np.zeros((N, N))), node_niter, t, t, gamma, xa, lam, lam, N)
+            out["mse_lists"][i].append(float(np.mean((x[i] - ph) ** 2)))
+            out["mse_sino_lists"][i].append(float(np.linalg.norm(ops[i].forward(x[i]) - b[i])))
+        t = 1.0 / norm_agg
+        x_agg, y1_agg, y2_agg = pdhg_steps(list(ops), adj_agg, b, x_agg, y1_agg, y2_agg, agg_niter, t, t, 0.0, None,
+                                           1.0, lambda_agg, N)
+        out["mse_agg_list"].append(float(np.mean((x_agg - ph) ** 2)))
+        out["mse_agg_sino_list"].append(float(math.sqrt(sum(np.sum((o.forward(x_agg) - bi) ** 2)
+                                                            for o, bi in zip(ops, b)))))
+    out["x_vars"], out["x_agg"] = x, x_agg
+    return out

@@ -112,3 +112,33 @@ def test_tv_pairing_quirk_is_documented_not_reproduced():
     rng = np.random.default_rng(1)
     x = rng.standard_normal(25)
     assert abs(O.tv_reference_pairing(x, 5) - O.tv_canonical(x, 5)) > 1e-3
+
+
+def test_pdhg_variant_pieces():
+    """PDHG consensus twin (ADMM_Tomo_Only.py:89-148): the gradient pair is an exact adjoint pair, the operator-norm
+    estimate bounds |L x| / |x|, and the aggregate PDHG iteration decreases its objective."""
+    N = 16
+    rng = np.random.default_rng(3)
+    x, p1, p2 = rng.standard_normal(N * N), rng.standard_normal((N, N)), rng.standard_normal((N, N))
+    g1, g2 = O.odl_grad(x, N)
+    assert abs((g1 * p1).sum() + (g2 * p2).sum() - x @ O.odl_grad_adjoint(p1, p2, N)) < 1e-10
+    # zero padding beyond the last index: the last row / column differences are -x / h
+    assert np.allclose(g1[-1], -x.reshape(N, N)[-1] * N / 2) and np.allclose(g2[:, -1], -x.reshape(N, N)[:, -1] * N / 2)
+    ops = [O.JosephOperator(N, t) for t in O.node_angles(24, 3)]
+    img = O.shepp_logan(N)
+    b = [o.forward(img) for o in ops]
+    adj = (np.pi / ops[0].nang) * (2.0 / N) / (2.0 / N) ** 2
+    nrm = O.pdhg_opnorm(ops[0], adj, N, 40)
+    for _ in range(5):
+        v = rng.standard_normal(N * N)
+        g1, g2 = O.odl_grad(v, N)
+        Lv2 = v @ (adj * ops[0].adjoint(ops[0].forward(v)) + O.odl_grad_adjoint(g1, g2, N))   # <v, L* L v>
+        assert np.sqrt(Lv2) <= nrm * np.linalg.norm(v) * (1 + 1e-3)
+
+    def objective(xv):
+        g1, g2 = O.odl_grad(xv, N)
+        return sum(np.sum((o.forward(xv) - bi) ** 2) for o, bi in zip(ops, b)) + 0.005 * np.sqrt(g1 ** 2 + g2 ** 2).sum()
+    r5 = O.pdhg_consensus(ops, b, img, N, niter=5)
+    r40 = O.pdhg_consensus(ops, b, img, N, niter=40)
+    assert objective(r40["x_agg"]) < objective(r5["x_agg"]) < objective(np.zeros(N * N))
+    assert r40["mse_agg_list"][-1] < r5["mse_agg_list"][-1]
