@@ -513,7 +513,8 @@ class ADMMEngine:
         st.reuse_ax = 0 if (self.k % self.ax_refresh_every == 0) else 1
         # likewise the CG residual: the TV pass and the rhs0 assembly carry r = rhs0 + tvterm - H x along, so a solve
         # starts without a back-projection; rebuilt from scratch on the refresh iterations
-        st.carry_r = 1 if self.carry_r else 0
+        # bit 0: a solve may take the carried residual; bit 1: its TV pass hands the residual on to the next solve
+        st.carry_r = 3 if self.carry_r else 0
         st.reuse_r = st.reuse_ax if self.carry_r == "always" else 0
         nat.check(L.admm_rhs0(h, sref, self.nbr_ptr.data_ptr(), self.nbr_z.data_ptr(), self.nbr_y.data_ptr(),
                               self.nbr_q.data_ptr(), 0, self.V, self._stream()), "admm_rhs0")
@@ -532,12 +533,14 @@ class ADMMEngine:
                 st.max_tighten, st.eps_target = self.max_tighten, eps_target
                 st.accept_mode, st.skip_mse = 1, (1 if self.max_tighten > 0 else 0)
                 nat.check(L.admm_x_update(h, sref, n0, nn, self.S, self.C, self._stream()), "admm_x_update")
-                keep = (st.reuse_ax, st.reuse_r)
-                st.masked, st.reuse_ax, st.reuse_r, st.accept_mode = 1, 1, st.carry_r, 2
+                keep = (st.reuse_ax, st.reuse_r, st.carry_r)
+                st.masked, st.reuse_ax, st.reuse_r, st.accept_mode = 1, 1, (1 if st.carry_r else 0), 2
                 for t in range(self.max_tighten):
                     last = (t == self.max_tighten - 1)
                     if self.carry_r == "first_retry":
                         st.reuse_r = 1 if (t == 0 and not last) else 0
+                    if last and self.carry_r and self.carry_r != "always":
+                        st.carry_r = 1      # the next iteration's first solve rebuilds r: this solve's TV pass need not hand it on
                     # sharded: x is final after the LAST retry's CG, so its TV pass (w, tvterm, |g| only) is held back and
                     # runs under the cut-edge exchange (tv_phase); needs the whole rank in one node group
                     st.defer_tv = 1 if (self._defer_last_tv and last) else 0
@@ -546,6 +549,8 @@ class ADMMEngine:
                 if not self._defer_last_tv:
                     st.masked, st.accept_mode = 0, 0
                 st.reuse_ax, st.reuse_r, st.skip_mse = keep[0], keep[1], 0
+                if not self._defer_last_tv:
+                    st.carry_r = keep[2]      # (a deferred last TV pass still needs this solve's setting: reset next iteration)
             if self.phases > 1:
                 if ph == self.phases - 1 and getattr(self, "time_exchange", False):
                     self._ex_t0 = self.torch.cuda.Event(enable_timing=True)
@@ -558,11 +563,18 @@ class ADMMEngine:
         retry solve, followed by the final acceptance bookkeeping)."""
         st = self.st
         L, h, sref = nat.lib(), self.plan.handle, ctypes.byref(self.st)
+        # flags: 1 diagnostics; 2 the solve's last CG update left r <- r - alpha Hp to this pass; 4 ... and r sits in r1
+        # (the fully fused CG ping-pongs r / r1 once per iteration after the first)
+        flags = 1
+        if self.C > 0:
+            flags |= 2
+            if int(st.fuse_pupdate) == 2 and (self.C - 1) % 2 == 1:
+                flags |= 4
         if self.acceptance:     # masked pass of the last retry solve; carries that solve's a14 bookkeeping (accept_mode 2)
-            nat.check(L.admm_tv_pass(h, sref, 0, self.V, 1, self._stream()), "admm_tv_pass")
+            nat.check(L.admm_tv_pass(h, sref, 0, self.V, flags, self._stream()), "admm_tv_pass")
             st.masked, st.defer_tv, st.accept_mode = 0, 0, 0
             return
-        nat.check(L.admm_tv_pass(h, sref, 0, self.V, 1, self._stream()), "admm_tv_pass")
+        nat.check(L.admm_tv_pass(h, sref, 0, self.V, flags, self._stream()), "admm_tv_pass")
 
     def exchange_start(self, phase=None):
         """Pack a = x + y of this rank's cut-edge ends (of exchange phase `phase`, or all).  NCCL mode: post the grouped

@@ -65,7 +65,7 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
                        cg_iters=2, tv_sweeps=1, tv_mu=None, node_prec=None, weighted_z=False, scs_eps=None,
                        check_every=1, node_group=None, fuse_pupdate=True, device=None, return_engine=False,
                        distributed=None, ax_refresh_every=10, exchange="auto", gather="all", exchange_phases=None, partition="auto",
-                       acceptance=True, max_tighten=2, carry_residual=False,
+                       acceptance=True, max_tighten=2, carry_residual="iteration",
                        **kwargs):
     """Returns x_per_node as list of reconstructions, each length n, and the history of residual norms
     (block_6_admm_loop_ver2.py:21-24).
@@ -88,6 +88,9 @@ def decentralized_admm(A_dense_list, sinograms, G, Wi_list, Qij_diag_fn,
     `exchange_phases` pieces as node blocks finish).  `partition`: node -> GPU map, "auto" (balanced min-cut
     for V <= 256), "mincut", "contiguous" ((i*G)//V) or an explicit list of ranks.  `gather`: "all" (every rank returns every node's x, like the single-process
     reference) or "rank0" (only rank 0 receives the full list; the others get their own nodes and None elsewhere).
+    `carry_residual`: "iteration" (default) -- the first solve of an outer iteration rebuilds the CG residual with a
+    back-projection, the a14 retry solves take the one the TV pass carried along; "first_retry", False (every solve
+    rebuilds it), "always" (carried across iterations too); measured trace errors in DESIGN.md section 3.
     """
     for k in list(kwargs):
         if k in _IGNORED:

@@ -458,8 +458,8 @@ extern "C" int admm_rhs0(admm_plan* p, const admm_state* s, const int* d_nbr_ptr
     R.atb = s->atb + off; R.rhs0 = s->rhs0 + off; R.nbr_ptr = d_nbr_ptr; R.nbr_z = d_nbr_z; R.nbr_y = d_nbr_y;
     R.nbr_q = d_nbr_q; R.stride = s->stride; R.n = (long long)p->N * p->N; R.node0 = node0; R.rho = s->rho;
     R.q_uniform = s->q_uniform;
-    if (s->carry_r && s->reuse_r) {   // the residual rides along: r += rhs0' - rhs0 ; p0 = r ; <r,r> -> S_RR0
-        R.r_upd = s->r + off; R.p_out = s->p0 + off;
+    if ((s->carry_r & 1) && s->reuse_r) {   // the residual rides along: r += rhs0' - rhs0 ; p0 = r ; <r,r> -> S_RR0
+        R.r_upd = s->r + off; R.p_out = (s->fuse_pupdate == 2) ? nullptr : s->p0 + off;
         R.part = s->part + (long long)node0 * admm_plan_info(p, ADMM_INFO_PART_FLOATS);
         R.counter = s->counter + node0; R.scal = s->scal;
     }
@@ -467,7 +467,7 @@ extern "C" int admm_rhs0(admm_plan* p, const admm_state* s, const int* d_nbr_ptr
     return ADMM_OK;
 }
 
-static TvParams make_tv(const admm_plan* p, const admm_state* s, int node0, bool diag, int parity) {
+static TvParams make_tv(const admm_plan* p, const admm_state* s, int node0, bool diag, int parity, bool hand_on) {
     TvParams T{};
     const long long off = (long long)node0 * s->stride;
     if (s->ctl) parity = 0;   // the per-node parity lives in ctl[node].wpar and is applied (and flipped) by the kernel
@@ -475,7 +475,11 @@ static TvParams make_tv(const admm_plan* p, const admm_state* s, int node0, bool
     float* wout = parity ? s->w0 : s->w1;
     T.x = s->x + off; T.w_in = win + 2 * off; T.w_out = wout + 2 * off; T.tvterm = s->tvterm + off;
     T.r = diag ? s->r + off : nullptr; T.xtrue = s->xtrue;
-    if (s->carry_r) { T.r_upd = s->r + off; T.p_out = s->p0 + off; } T.stride = s->stride; T.node0 = node0; T.N = p->N;
+    // carry_r bit 1: this pass hands r = rhs0 + tvterm' - H x to the next solve (bit 0, in admm_x_update: the solve takes
+    // the carried residual).  With the fully fused CG the start direction p0 = r is not materialised: it IS the r buffer
+    T.hp = nullptr;   // set by the caller when the solve's last CG update left its r half pending
+    if (hand_on) { T.r_upd = s->r + off; T.p_out = (s->fuse_pupdate == 2) ? nullptr : s->p0 + off; }
+    T.stride = s->stride; T.node0 = node0; T.N = p->N;
     T.lam = s->lam; T.mu = s->mu;
     T.part = s->part + (long long)node0 * admm_plan_info(p, ADMM_INFO_PART_FLOATS);
     T.counter = s->counter + node0; T.scal = s->scal;
@@ -488,7 +492,11 @@ static TvParams make_tv(const admm_plan* p, const admm_state* s, int node0, bool
 extern "C" int admm_tv_pass(admm_plan* p, admm_state* s, int node0, int nodes, int with_diag, void* stream) {
     if (int e = check_nodes(p, node0, nodes)) return e;
     if (!s) return fail(ADMM_ERR_ARG, "admm_tv_pass: null state");
-    TvParams T = make_tv(p, s, node0, with_diag != 0, s->w_parity);
+    TvParams T = make_tv(p, s, node0, with_diag != 0, s->w_parity, (s->carry_r & 2) != 0);
+    if (with_diag & 2) {   // deferred pass of a solve that ran CG iterations: r <- r - alpha Hp is still pending
+        T.hp = s->hp + (long long)node0 * s->stride;
+        if (with_diag & 4) T.r = s->r1 + (long long)node0 * s->stride;   // ... and the fused CG's ping-pong left r in r1
+    }
     if (s->ctl && with_diag) T.accept = s->accept_mode;   // a deferred pass that ends a solve carries the a14 decision
     CK(launch_tv(T, nodes, (cudaStream_t)stream));
     return ADMM_OK;
@@ -524,16 +532,23 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
         }
         BackParams B = make_back(p, s->ax, s->prec, s->r + off, s->stride, node0);
         B.v = s->x + off; B.rhoD_vec = s->rhoD_vec ? s->rhoD_vec + off : nullptr; B.rhoD_s = s->rhoD_s; B.mu = s->mu;
-        B.rhs0 = s->rhs0 + off; B.tvterm = s->tvterm + off; B.p_out = s->p0 + off;
+        // fully fused CG: r ping-pongs (r -> r1 -> r ...), so the buffer holding r at the start of the solve stays intact
+        // until the fused step of iteration 1 has read it as the old direction: p0 = r need not be written
+        const bool direct_p = (s->fuse_pupdate == 2);
+        B.rhs0 = s->rhs0 + off; B.tvterm = s->tvterm + off; B.p_out = direct_p ? nullptr : s->p0 + off;
         B.part = part; B.counter = counter; B.scal = s->scal; B.dot_slot = S_RR0; B.ctl = mask;
         // with carry_r the TV pass (r += tvterm' - tvterm) and the rhs0 assembly (r += rhs0' - rhs0) keep r = rhs0 +
         // tvterm - H x, p0 = r and <r,r> current, so the solve starts without this back-projection
-        if (!(s->carry_r && (sw > 0 || s->reuse_r))) CK(plan_back(p, BACK_RESID0, B, nodes, st));
+        if (!((s->carry_r & 1) && (sw > 0 || s->reuse_r))) CK(plan_back(p, BACK_RESID0, B, nodes, st));
         int cur = 0;
         float* rcur = s->r + off;            // residual buffer currently holding r (fuse 2 ping-pongs r / r1)
+        bool pending_r = false;              // the last CG update left r <- r - alpha Hp to the TV pass
+        float* r_where = rcur;
         for (int it = 0; it < cg_iters; ++it) {
             const int rr_in = (it & 1) ? S_RR1 : S_RR0, rr_out = (it & 1) ? S_RR0 : S_RR1;
-            float* pcur = (cur ? s->p1 : s->p0) + off;
+            // direct_p: iteration 0 projects r itself, iteration 1's fused step reads it (rcur is still that buffer) as the
+            // old direction and writes p' to p1; from then on p1 / p0 ping-pong as usual
+            float* pcur = (it <= 1 && direct_p) ? rcur : (cur ? s->p1 : s->p0) + off;
             float* poth = (cur ? s->p0 : s->p1) + off;
             if (it > 0 && s->fuse_pupdate == 2) {
                 // x += alpha p ; r' = r - alpha Hp ; p' = r' + beta p ; <r',r'> -> rr_in  -- all inside the projector
@@ -580,13 +595,20 @@ extern "C" int admm_x_update(admm_plan* p, admm_state* s, int node0, int nodes, 
                 U.x = s->x + off; U.r = s->r + off; U.r_in = rcur; U.p = pcur; U.hp = s->hp + off; U.stride = s->stride;
                 U.n = n; U.node0 = node0; U.rr_in = rr_in; U.rr_out = rr_out; U.part = part; U.counter = counter;
                 U.scal = s->scal; U.ctl = mask;
+                // the solve's last update: x only; the TV pass that ends the sweep (here or deferred) applies r -= alpha Hp,
+                // reading r where the CG left it (the fused form's ping-pong: r or r1) and writing the carried one to s->r
+                U.x_only = last ? 1 : 0;
+                if (last) { pending_r = true; r_where = rcur; }
                 long long nb = (n / 4 + 256 * 4 - 1) / (256 * 4);
                 nb = std::max(1LL, std::min(nb, 4096LL));
                 CK(launch_cg_update(U, nodes, (int)nb, st));
             }
         }
         if (!(s->defer_tv && sw == sweeps - 1)) {
-            TvParams T = make_tv(p, s, node0, true, parity);
+            // hand the residual on to the next solve (bit 1), and always to the next sweep of THIS solve when sweeps carry
+            const bool hand_on = (s->carry_r & 2) || ((s->carry_r & 1) && sw < sweeps - 1);
+            TvParams T = make_tv(p, s, node0, true, parity, hand_on);
+            if (pending_r) { T.hp = s->hp + off; T.r = r_where; }
             if (s->ctl && sw == sweeps - 1) T.accept = s->accept_mode;   // the a14 decision rides on the solve's last TV pass
             CK(launch_tv(T, nodes, st));
             parity ^= 1;

@@ -298,25 +298,31 @@ fwd_strip_kernel(const __grid_constant__ FwdParams P) {
         lds_pair(addr, a, b);                                                               \
         acc += fmaf(f, b - a, a);                                                           \
     }
-                for (; k + 7 <= khi; k += 8) {
-                    const float ub = fmaf(-kf, s, u0);
-                    const f32x2 ub2 = pack2(ub, ub - s);
-#pragma unroll
-                    for (int q = 0; q < 8; q += 2) {
-                        const f32x2 uu = (q == 0) ? ub2 : fma2(s2, splat2(-(float)q), ub2);
-                        const f32x2 fi = add2_rm(uu, splat2(kMagic));
-                        const f32x2 f = sub2(uu, sub2(fi, splat2(kMagic)));
-                        float fia, fib;
-                        unpack2(fi, fia, fib);
-                        float a0, b0, a1, b1;
-                        lds_pair((__float_as_uint(fia) << 2) + rowa + (unsigned)(q * PITCH * 4), a0, b0);
-                        lds_pair((__float_as_uint(fib) << 2) + rowa + (unsigned)((q + 1) * PITCH * 4), a1, b1);
-                        const f32x2 av = pack2(a0, a1);
-                        acc2 = add2(acc2, fma2(f, sub2(pack2(b0, b1), av), av));
-                    }
-                    kf += 8.f;
-                    rowa += 8 * PITCH * 4;
-                }
+#define FWD_PAIRS(NSTEP)                                                                                    \
+    {                                                                                                       \
+        const float ub = fmaf(-kf, s, u0);                                                                  \
+        const f32x2 ub2 = pack2(ub, ub - s);                                                                \
+        _Pragma("unroll") for (int q = 0; q < (NSTEP); q += 2) {                                            \
+            const f32x2 uu = (q == 0) ? ub2 : fma2(s2, splat2(-(float)q), ub2);                             \
+            const f32x2 fi = add2_rm(uu, splat2(kMagic));                                                   \
+            const f32x2 f = sub2(uu, sub2(fi, splat2(kMagic)));                                             \
+            float fia, fib;                                                                                 \
+            unpack2(fi, fia, fib);                                                                          \
+            float a0, b0, a1, b1;                                                                           \
+            lds_pair((__float_as_uint(fia) << 2) + rowa + (unsigned)(q * PITCH * 4), a0, b0);               \
+            lds_pair((__float_as_uint(fib) << 2) + rowa + (unsigned)((q + 1) * PITCH * 4), a1, b1);         \
+            const f32x2 av = pack2(a0, a1);                                                                 \
+            acc2 = add2(acc2, fma2(f, sub2(pack2(b0, b1), av), av));                                        \
+        }                                                                                                   \
+        kf += (float)(NSTEP);                                                                               \
+        rowa += (NSTEP) * PITCH * 4;                                                                        \
+        k += (NSTEP);                                                                                       \
+    }
+                while (k + 7 <= khi) FWD_PAIRS(8)
+                // tail: one 4-step and one 2-step packed block before the (at most one) single step
+                if (k + 3 <= khi) FWD_PAIRS(4)
+                if (k + 1 <= khi) FWD_PAIRS(2)
+#undef FWD_PAIRS
                 for (; k <= khi; ++k) {
                     const float u = fmaf(-kf, s, u0);
                     FWD_SAMPLE(u, 0u)
@@ -564,7 +570,7 @@ back_tile_kernel(const __grid_constant__ BackParams P) {
                     } else { const float rr = rh[px] - hv; res[px] = rr; dsum = fmaf(rr, rr, dsum); }
                 }
                 st4(P.out + nb + g, make_float4(res[0], res[1], res[2], res[3]));
-                if (MODE == BACK_RESID0) st4(P.p_out + nb + g, make_float4(res[0], res[1], res[2], res[3]));
+                if (MODE == BACK_RESID0 && P.p_out) st4(P.p_out + nb + g, make_float4(res[0], res[1], res[2], res[3]));
             } else if (rowok && iy < N) {
                 float vc[6], vu[4], vd[4];  // centre row with one halo each side, up row, down row
 #pragma unroll
@@ -604,12 +610,12 @@ back_tile_kernel(const __grid_constant__ BackParams P) {
                 float* o = P.out + nb + g;
                 if (iy + 3 < N && vecok) {
                     st4(o, make_float4(res[0], res[1], res[2], res[3]));
-                    if (MODE == BACK_RESID0) st4(P.p_out + nb + g, make_float4(res[0], res[1], res[2], res[3]));
+                    if (MODE == BACK_RESID0 && P.p_out) st4(P.p_out + nb + g, make_float4(res[0], res[1], res[2], res[3]));
                 } else {
                     for (int px = 0; px < 4; ++px)
                         if (iy + px < N) {
                             o[px] = res[px];
-                            if (MODE == BACK_RESID0) P.p_out[nb + g + px] = res[px];
+                            if (MODE == BACK_RESID0 && P.p_out) P.p_out[nb + g + px] = res[px];
                         }
                 }
             }

@@ -93,7 +93,7 @@ struct BackParams {
     float mu;
     const float* rhs0;       // BACK_RESID0
     const float* tvterm;     // BACK_RESID0
-    float* p_out;            // BACK_RESID0: p = r
+    float* p_out;            // BACK_RESID0: p = r  (nullptr: not materialised -- the CG takes r itself as its first direction)
     // reduction workspace
     float* part;             // [V][nblk] partials
     unsigned* counter;       // [V]
@@ -118,6 +118,7 @@ enum ScalSlot : int {
     S_GN2 = 6,              // |g|^2 stationarity
     S_IMG = 7,              // |x - x_true|^2
     S_MSE = 8,              // |Ax - b|^2
+    S_ALPHA = 9,            // CG step length of the solve's last iteration, pending for r (cg_update x_only -> TV pass)
     S_SCRATCH = 15          // sink for reductions whose result is not wanted
 };
 

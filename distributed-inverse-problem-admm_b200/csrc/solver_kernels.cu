@@ -1,6 +1,8 @@
 // solver_kernels.cu -- K3 fused TV stencil, K4 CG vector updates with in-kernel reductions, K5 edge
 // (consensus z / dual y / residual) kernel, K6 right-hand-side assembly, and the small per-iteration
 // bookkeeping kernels.  sm_100a.  All are single-pass streaming kernels (HBM-bound).
+#include <cstdlib>
+
 #include "solver_kernels.cuh"
 
 namespace admm {
@@ -78,8 +80,8 @@ __device__ __forceinline__ void load_seg(const float* __restrict__ row, int c, i
 template <bool INTR>
 __device__ __forceinline__ void tv_quad(const TvParams& P, const float* __restrict__ x, const float* __restrict__ w1p,
                                         const float* __restrict__ w2p, float* __restrict__ wo1, float* __restrict__ wo2,
-                                        long long nb, int N, int r, int c0, float kappa, float& tv, float& gn2, float& img,
-                                        float& rr) {
+                                        long long nb, int N, int r, int c0, float kappa, float alpha, float& tv, float& gn2,
+                                        float& img, float& rr) {
     const bool vec = INTR || ((N & 3) == 0);   // then c0 + 3 < N and rows are 16-byte aligned
     const long long g0 = (long long)r * N + c0;
     float xm[5], xc[6], xp[5], wc1[5], wc2[5], wu1[4], wu2[4];
@@ -136,12 +138,20 @@ __device__ __forceinline__ void tv_quad(const TvParams& P, const float* __restri
     float told[4], rc[4], xt[4];
     const bool diag = (P.r != nullptr);
     const bool upd = (P.r_upd != nullptr);
-    const float* rsrc = upd ? P.r_upd : P.r;
+    const float* rsrc = P.r ? P.r : P.r_upd;    // read where the CG left r; the carried one is written to r_upd
     float* __restrict__ tvt = P.tvterm + nb;
     if (vec) {
         const float4 t4 = ld4(tvt + g0);
         told[0] = t4.x; told[1] = t4.y; told[2] = t4.z; told[3] = t4.w;
-        if (diag || upd) { const float4 q = ld4(rsrc + nb + g0); rc[0] = q.x; rc[1] = q.y; rc[2] = q.z; rc[3] = q.w; }
+        if (diag || upd) {
+            const float4 q = ld4(rsrc + nb + g0);
+            rc[0] = q.x; rc[1] = q.y; rc[2] = q.z; rc[3] = q.w;
+            if (P.hp) {      // the pending half of the last CG update: r <- r - alpha Hp
+                const float4 h4 = ld4(P.hp + nb + g0);
+                rc[0] = fmaf(-alpha, h4.x, rc[0]); rc[1] = fmaf(-alpha, h4.y, rc[1]);
+                rc[2] = fmaf(-alpha, h4.z, rc[2]); rc[3] = fmaf(-alpha, h4.w, rc[3]);
+            }
+        }
         if (P.xtrue) { const float4 q = ld4(P.xtrue + g0); xt[0] = q.x; xt[1] = q.y; xt[2] = q.z; xt[3] = q.w; }
     } else {
 #pragma unroll
@@ -149,6 +159,7 @@ __device__ __forceinline__ void tv_quad(const TvParams& P, const float* __restri
             const bool ok = c0 + k < N;
             told[k] = ok ? tvt[g0 + k] : 0.f;
             rc[k] = (ok && (diag || upd)) ? rsrc[nb + g0 + k] : 0.f;
+            if (ok && (diag || upd) && P.hp) rc[k] = fmaf(-alpha, P.hp[nb + g0 + k], rc[k]);
             xt[k] = (ok && P.xtrue) ? P.xtrue[g0 + k] : 0.f;
         }
     }
@@ -206,19 +217,135 @@ __device__ __forceinline__ void tv_quad(const TvParams& P, const float* __restri
         st4(tvt + g0, make_float4(tvo[0], tvo[1], tvo[2], tvo[3]));
         if (upd) {
             st4(P.r_upd + nb + g0, make_float4(rn[0], rn[1], rn[2], rn[3]));
-            st4(P.p_out + nb + g0, make_float4(rn[0], rn[1], rn[2], rn[3]));
+            if (P.p_out) st4(P.p_out + nb + g0, make_float4(rn[0], rn[1], rn[2], rn[3]));
         }
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (c0 + k < N) {
                 wo1[g0 + k] = w1o[k]; wo2[g0 + k] = w2o[k]; tvt[g0 + k] = tvo[k];
-                if (upd) { P.r_upd[nb + g0 + k] = rn[k]; P.p_out[nb + g0 + k] = rn[k]; }
+                if (upd) { P.r_upd[nb + g0 + k] = rn[k]; if (P.p_out) P.p_out[nb + g0 + k] = rn[k]; }
             }
     }
 }
 
-__global__ void __launch_bounds__(TVX * TVY, 4)
+// Interior blocks march down the rows: thread (lane, band) owns the 4 columns c0..c0+3 of TVROWS consecutive rows.  The
+// (d - w') and the unit gradient of row r ARE the "upper neighbour" values of row r + 1, so they are carried in
+// registers instead of being recomputed (5.5 shrink + unit-gradient evaluations per 4 pixels instead of 9), x rows
+// rotate through registers (one new x row per step).  Per pixel the operations and their order are those of tv_quad<true>: results are bit-identical.
+constexpr int TVROWS = 8;
+
+__device__ __forceinline__ void tv_strip(const TvParams& P, const float* __restrict__ x, const float* __restrict__ w1p,
+                                         const float* __restrict__ w2p, float* __restrict__ wo1, float* __restrict__ wo2,
+                                         long long nb, int N, int r0, int c0, float kappa, float alpha, float& tv, float& gn2,
+                                         float& img, float& rr) {
+    const bool diag = (P.r != nullptr);
+    const bool upd = (P.r_upd != nullptr);
+    const float* rsrc = P.r ? P.r : P.r_upd;    // read where the CG left r; the carried one is written to r_upd
+    float* __restrict__ tvt = P.tvterm + nb;
+    long long g0 = (long long)r0 * N + c0;
+    // prologue: rows r0 - 1 and r0, and the upper-neighbour values of row r0
+    float xm[4], xc[6], dwx_up[4], px_up[4];
+    {
+        const float4 a = ld4(x + g0 - N), q = ld4(x + g0);
+        const float a4 = x[g0 - N + 4];
+        const float4 u1 = ld4(w1p + g0 - N), u2 = ld4(w2p + g0 - N);
+        xm[0] = a.x; xm[1] = a.y; xm[2] = a.z; xm[3] = a.w;
+        xc[0] = x[g0 - 1]; xc[1] = q.x; xc[2] = q.y; xc[3] = q.z; xc[4] = q.w; xc[5] = x[g0 + 4];
+        const float xm5[5] = {a.x, a.y, a.z, a.w, a4};
+        const float wu1[4] = {u1.x, u1.y, u1.z, u1.w}, wu2[4] = {u2.x, u2.y, u2.z, u2.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gxu = xc[k + 1] - xm5[k], gyu = xm5[k + 1] - xm5[k];
+            dwx_up[k] = shrink_dw(gxu, gyu, wu1[k], wu2[k], kappa).dwx;
+            float pyu, mg;
+            unit_grad(gxu, gyu, px_up[k], pyu, mg);
+        }
+    }
+    // loads of one row: x of the row below (c0-1 .. c0+4), w (c0-1 .. c0+3), tvterm, r, x_true
+    struct Row { float4 xp, w1, w2; float xpl, xpr, w1l, w2l; };
+    auto load_row = [&](long long g) {
+        Row R;
+        R.xp = ld4(x + g + N); R.xpl = x[g + N - 1]; R.xpr = x[g + N + 4];
+        R.w1 = ld4(w1p + g); R.w2 = ld4(w2p + g); R.w1l = w1p[g - 1]; R.w2l = w2p[g - 1];
+        return R;
+    };
+#pragma unroll 1
+    for (int i = 0; i < TVROWS; ++i, g0 += N) {
+        const Row cur = load_row(g0);
+        // consumed at the end of the per-pixel arithmetic: issued here, no extra registers across iterations
+        const float4 t4 = ld4(tvt + g0);
+        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f), x4 = r4;
+        if (diag || upd) {
+            r4 = ld4(rsrc + nb + g0);
+            if (P.hp) {
+                const float4 h4 = ld4(P.hp + nb + g0);
+                r4.x = fmaf(-alpha, h4.x, r4.x); r4.y = fmaf(-alpha, h4.y, r4.y);
+                r4.z = fmaf(-alpha, h4.z, r4.z); r4.w = fmaf(-alpha, h4.w, r4.w);
+            }
+        }
+        if (P.xtrue) x4 = ld4(P.xtrue + g0);
+        const float xp[6] = {cur.xpl, cur.xp.x, cur.xp.y, cur.xp.z, cur.xp.w, cur.xpr};
+        const float wc1[5] = {cur.w1l, cur.w1.x, cur.w1.y, cur.w1.z, cur.w1.w};
+        const float wc2[5] = {cur.w2l, cur.w2.x, cur.w2.y, cur.w2.z, cur.w2.w};
+        const float told[4] = {t4.x, t4.y, t4.z, t4.w};
+        const float rc[4] = {r4.x, r4.y, r4.z, r4.w};
+        const float xt[4] = {x4.x, x4.y, x4.z, x4.w};
+        float dwy_prev, py_prev;
+        {
+            const float gx = xp[0] - xc[0], gy = xc[1] - xc[0];
+            dwy_prev = shrink_dw(gx, gy, wc1[0], wc2[0], kappa).dwy;
+            float pxl, mg;
+            unit_grad(gx, gy, pxl, py_prev, mg);
+        }
+        float w1o[4], w2o[4], tvo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float xcv = xc[k + 1];
+            const float gx = xp[k + 1] - xcv, gy = xc[k + 2] - xcv;
+            const Dw o = shrink_dw(gx, gy, wc1[k + 1], wc2[k + 1], kappa);
+            float kt = dwx_up[k];
+            kt -= o.dwx;
+            kt += dwy_prev;
+            kt -= o.dwy;
+            float pxo, pyo, mag;
+            unit_grad(gx, gy, pxo, pyo, mag);
+            tv += mag;
+            if (diag) {
+                float lap = 0.f;
+                lap += xcv - xm[k];
+                lap += xcv - xp[k + 1];
+                lap += xcv - xc[k];
+                lap += xcv - xc[k + 2];
+                float dv = 0.f;
+                dv += px_up[k] - pxo;
+                dv += py_prev - pyo;
+                const float gv = told[k] - rc[k] - P.mu * lap + P.lam * dv;
+                gn2 = fmaf(gv, gv, gn2);
+            }
+            if (P.xtrue) { const float e = xcv - xt[k]; img = fmaf(e, e, img); }
+            w1o[k] = o.w1; w2o[k] = o.w2; tvo[k] = P.mu * kt;
+            dwy_prev = o.dwy; py_prev = pyo;
+            dwx_up[k] = o.dwx; px_up[k] = pxo;      // the row below sees this row as its upper neighbour
+        }
+        st4(wo1 + g0, make_float4(w1o[0], w1o[1], w1o[2], w1o[3]));
+        st4(wo2 + g0, make_float4(w2o[0], w2o[1], w2o[2], w2o[3]));
+        st4(tvt + g0, make_float4(tvo[0], tvo[1], tvo[2], tvo[3]));
+        if (upd) {
+            float rn[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { rn[k] = rc[k] + (tvo[k] - told[k]); rr = fmaf(rn[k], rn[k], rr); }
+            st4(P.r_upd + nb + g0, make_float4(rn[0], rn[1], rn[2], rn[3]));
+            if (P.p_out) st4(P.p_out + nb + g0, make_float4(rn[0], rn[1], rn[2], rn[3]));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xm[k] = xc[k + 1];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) xc[k] = xp[k];
+    }
+}
+
+__global__ void __launch_bounds__(TVX * TVY, 3)
 tv_fused_kernel(const TvParams P) {
     __shared__ __align__(16) float red[128];
     const int N = P.N;
@@ -226,7 +353,7 @@ tv_fused_kernel(const TvParams P) {
     if (P.masked && !P.ctl[node].active) return;   // a14 retry pass: this node was accepted already
     const long long nb = (long long)blockIdx.z * P.stride;
     const long long n = (long long)N * N;
-    const int r = blockIdx.y * TVY + threadIdx.y;
+    const int r0 = (blockIdx.y * TVY + threadIdx.y) * TVROWS;   // first of this thread's TVROWS rows
     const int c0 = (blockIdx.x * TVX + threadIdx.x) * 4;
     const float* __restrict__ x = P.x + nb;
     // device-side ping-pong parity of this node's multiplier (host parity when there is no control table): every block
@@ -237,12 +364,17 @@ tv_fused_kernel(const TvParams P) {
     float* __restrict__ wo1 = (swap ? const_cast<float*>(P.w_in) : P.w_out) + 2 * nb;
     float* __restrict__ wo2 = wo1 + n;
     const float kappa = P.lam / P.mu;
+    const float alpha = P.hp ? (float)P.scal[(long long)node * NSCAL + S_ALPHA] : 0.f;
     float tv = 0.f, gn2 = 0.f, img = 0.f, rr = 0.f;
-    // block-uniform: rows [by*TVY, +TVY) and columns [bx*4*TVX, +4*TVX) all strictly inside the image
-    const bool interior = ((N & 3) == 0) && blockIdx.y >= 1 && (int)(blockIdx.y + 1) * TVY <= N - 1 &&
+    // block-uniform: rows [by*TVY*TVROWS, +TVY*TVROWS) and columns [bx*4*TVX, +4*TVX) all strictly inside the image
+    const bool interior = ((N & 3) == 0) && blockIdx.y >= 1 && (int)(blockIdx.y + 1) * TVY * TVROWS <= N - 1 &&
                           blockIdx.x >= 1 && (int)(blockIdx.x + 1) * 4 * TVX <= N - 1;
-    if (interior) tv_quad<true>(P, x, w1p, w2p, wo1, wo2, nb, N, r, c0, kappa, tv, gn2, img, rr);
-    else if (r < N && c0 < N) tv_quad<false>(P, x, w1p, w2p, wo1, wo2, nb, N, r, c0, kappa, tv, gn2, img, rr);
+    if (interior && P.strip) tv_strip(P, x, w1p, w2p, wo1, wo2, nb, N, r0, c0, kappa, alpha, tv, gn2, img, rr);
+    else if (interior) {
+        for (int r = r0; r < r0 + TVROWS; ++r) tv_quad<true>(P, x, w1p, w2p, wo1, wo2, nb, N, r, c0, kappa, alpha, tv, gn2, img, rr);
+    } else if (c0 < N) {
+        for (int r = r0; r < min(r0 + TVROWS, N); ++r) tv_quad<false>(P, x, w1p, w2p, wo1, wo2, nb, N, r, c0, kappa, alpha, tv, gn2, img, rr);
+    }
     float v[4] = {tv, gn2, img, rr};
     block_sum<4>(v, red);
     const int nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
@@ -276,9 +408,24 @@ cg_update_kernel(const CgParams P) {
     const float alpha = (php > 0.0) ? (float)(rr / php) : 0.f;
     const long long nb = (long long)blockIdx.y * P.stride;
     float* __restrict__ x = P.x + nb;
+    if (P.x_only) {      // launch-uniform: the r half of the update rides in the TV pass that follows
+        if (blockIdx.x == 0 && threadIdx.x == 0) P.scal[(long long)node * NSCAL + S_ALPHA] = (double)alpha;
+        const float* __restrict__ pp = P.p + nb;
+        const long long m4 = ((P.n & 3) == 0 && (P.stride & 3) == 0) ? (P.n >> 2) : 0;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m4; i += (long long)gridDim.x * blockDim.x) {
+            float4 xv = ld4(x + 4 * i);
+            const float4 pv = ld4(pp + 4 * i);
+            xv.x = fmaf(alpha, pv.x, xv.x); xv.y = fmaf(alpha, pv.y, xv.y);
+            xv.z = fmaf(alpha, pv.z, xv.z); xv.w = fmaf(alpha, pv.w, xv.w);
+            st4(x + 4 * i, xv);
+        }
+        for (long long i = 4 * m4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += (long long)gridDim.x * blockDim.x)
+            x[i] = fmaf(alpha, pp[i], x[i]);
+        return;
+    }
     float* r = P.r + nb;
     const float* rin = (P.r_in ? P.r_in : P.r) + nb;
-    const float* __restrict__ p = P.p + nb;
+    const float* p = P.p + nb;       // may BE the residual buffer (first CG iteration of the fully fused form: p = r)
     const float* __restrict__ hp = P.hp + nb;
     float s = 0.f;
     const long long n4 = ((P.n & 3) == 0 && (P.stride & 3) == 0) ? (P.n >> 2) : 0;   // float4 only when every node image is 16-byte aligned
@@ -379,7 +526,7 @@ rhs0_kernel(const RhsParams P) {
     float* out = P.rhs0 + nb;
     const bool upd = (P.r_upd != nullptr);
     float* rio = upd ? P.r_upd + nb : nullptr;
-    float* po = upd ? P.p_out + nb : nullptr;
+    float* po = (upd && P.p_out) ? P.p_out + nb : nullptr;
     float rr = 0.f;
     const long long n4 = ((P.n & 3) == 0 && (P.stride & 3) == 0) ? (P.n >> 2) : 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -399,7 +546,7 @@ rhs0_kernel(const RhsParams P) {
             const float4 od = ld4(out + 4 * i), rv = ld4(rio + 4 * i);
             const float4 rn = make_float4(rv.x + (nw.x - od.x), rv.y + (nw.y - od.y), rv.z + (nw.z - od.z), rv.w + (nw.w - od.w));
             st4(rio + 4 * i, rn);
-            st4(po + 4 * i, rn);
+            if (po) st4(po + 4 * i, rn);
             rr = fmaf(rn.x, rn.x, rr); rr = fmaf(rn.y, rn.y, rr); rr = fmaf(rn.z, rn.z, rr); rr = fmaf(rn.w, rn.w, rr);
         }
         st4(out + 4 * i, nw);
@@ -416,7 +563,7 @@ rhs0_kernel(const RhsParams P) {
         const float nw = atb[i] + cons;
         if (upd) {
             const float rn = rio[i] + (nw - out[i]);
-            rio[i] = rn; po[i] = rn; rr = fmaf(rn, rn, rr);
+            rio[i] = rn; if (po) po[i] = rn; rr = fmaf(rn, rn, rr);
         }
         out[i] = nw;
     }
@@ -630,8 +777,11 @@ static inline int stream_blocks(long long n, int per_thread) {
     return (int)b;
 }
 
-cudaError_t launch_tv(const TvParams& P, int nodes, cudaStream_t st) {
-    dim3 grid((P.N + 4 * TVX - 1) / (4 * TVX), (P.N + TVY - 1) / TVY, nodes);
+cudaError_t launch_tv(const TvParams& P0, int nodes, cudaStream_t st) {
+    static const int strip = [] { const char* e = getenv("ADMM_B200_TVSTRIP"); return (e && e[0] == '0') ? 0 : 1; }();
+    TvParams P = P0;
+    P.strip = strip;
+    dim3 grid((P.N + 4 * TVX - 1) / (4 * TVX), (P.N + TVY * TVROWS - 1) / (TVY * TVROWS), nodes);
     { ProfScope ps(KC_TV, st); tv_fused_kernel<<<grid, dim3(TVX, TVY), 0, st>>>(P); }
     return cudaGetLastError();
 }

@@ -12,7 +12,7 @@ struct TvParams {
     const float* r;        // [nodes][n] final CG residual (nullptr: skip the stationarity diagnostic)
     float* r_upd;          // [nodes][n] or nullptr: carry the residual to the next solve without a back-projection --
                            //   r += tvterm' - tvterm ; p_out = r ; <r,r> -> scal[S_RR0]   (r = rhs0 + tvterm - H x stays true)
-    float* p_out;          // [nodes][n] CG start direction (with r_upd)
+    float* p_out;          // [nodes][n] CG start direction (with r_upd); nullptr: not materialised (the CG starts from r itself)
     const float* xtrue;    // [n] or nullptr
     long long stride;
     int node0, N;
@@ -25,6 +25,10 @@ struct TvParams {
     int accept, max_tighten;
     double eps_target2;
     const int* iter_dev;
+    int strip;             // 1: interior blocks take the row-marching path (ADMM_B200_TVSTRIP=0 keeps the per-row form)
+    // the solve's last CG update is split: cg_update_kernel (x_only) did x += alpha p and left alpha in scal[S_ALPHA];
+    // this pass applies the other half, r <- r - alpha Hp, on the fly (hp != nullptr), so r is streamed once, not twice
+    const float* hp;
 };
 
 struct CgParams {
@@ -34,6 +38,7 @@ struct CgParams {
     int node0, rr_in, rr_out;
     float* part; unsigned* counter; double* scal;
     const NodeCtl* ctl;    // masked launches: skip inactive nodes (nullptr: all nodes)
+    int x_only;            // 1: x += alpha p only; alpha -> scal[S_ALPHA] (the TV pass that follows updates r, see TvParams::hp)
 };
 
 struct SinoParams {

@@ -77,9 +77,11 @@ typedef struct admm_state {
     struct admm_node_ctl* ctl; /* [V] per-node control words of the a14 accept / tighten rule, or NULL.  When set, the
                                  TV-multiplier parity is per node and device-resident (w_parity is ignored)   */
     int masked;               /* 1: admm_x_update / admm_tv_pass skip the nodes whose ctl[].active is 0 (retry pass) */
-    int carry_r;              /* 1: the TV pass also carries the CG residual to the next solve (r += tvterm' - tvterm,
-                                 p0 = r, <r,r>), and so does admm_rhs0 when reuse_r is set (r += rhs0' - rhs0): a solve
-                                 then starts without the A^T(P A x) back-projection of its residual                  */
+    int carry_r;              /* bit mask.  bit 1 (2): the TV pass that ends a solve also hands the CG residual to the next
+                                 solve (r += tvterm' - tvterm, <r,r>; p0 = r too unless fuse_pupdate == 2, where the CG takes
+                                 the r buffer itself as its first direction).  bit 0 (1): a solve with reuse_r set (and every
+                                 sweep after the first) takes that residual instead of rebuilding it with the A^T(P A x)
+                                 back-projection; admm_rhs0 then keeps it current too (r += rhs0' - rhs0)              */
     int reuse_r;              /* 1: r, p0 and <r,r> are current for the solve that follows (set 0 periodically, and for
                                  the first solve, to rebuild r = rhs0 + tvterm - H x and stop fp32 drift)             */
     int* iter_dev;            /* device-resident outer iteration counter k, or NULL.  When set (CUDA-graph replay of the
@@ -206,7 +208,10 @@ int admm_finalize(admm_plan* plan, const admm_state* st, const double* d_sums, c
                   int Vg, double* d_row, void* stream);
 
 /* ---- block_4 helpers on device (block_4_tv_helpers.py:17-46): one TV pass without a CG solve ------------
- * used by the drop-in block_4 module; outputs w', tvterm' and TV(x) like the fused K3. */
+ * used by the drop-in block_4 module; outputs w', tvterm' and TV(x) like the fused K3.  Also the deferred last pass of a
+ * solve (st->defer_tv).  with_diag is a bit mask: 1 stationarity / metrics diagnostics; 2 the solve's last CG update left
+ * its residual half, r <- r - alpha Hp, to this pass (admm_x_update with cg_iters > 0 always does; alpha sits in
+ * scal[S_ALPHA]); 4 that residual is in st->r1, not st->r (fuse_pupdate == 2 and an even cg_iters). */
 int admm_tv_pass(admm_plan* plan, admm_state* st, int node0, int nodes, int with_diag, void* stream);
 
 /* ---- peer-memory exchange buffers (CUDA IPC; one process per GPU) -----------------------------------------------

@@ -50,7 +50,7 @@ void orc_set_num_threads(int n) {
 void orc_forward(const double* X, int N, int D, double det_w, const double* cs, const double* sn,
                  int nang, double* out) {
     const double h = 2.0 / N, ds = det_w / D, smin = -0.5 * det_w, x0 = -1.0 + 0.5 * h;
-#pragma omp parallel for collapse(2) schedule(dynamic, 16)
+#pragma omp parallel for collapse(2) schedule(dynamic, 16) if (N >= 48)
     for (int a = 0; a < nang; ++a) {
         for (int j = 0; j < D; ++j) {
             const double c = cs[a], s = sn[a];
@@ -91,7 +91,7 @@ void orc_forward(const double* X, int N, int D, double det_w, const double* cs, 
 static void adjoint_impl(const double* q, int N, int D, double det_w, const double* cs,
                          const double* sn, int nang, int power, double* out) {
     const double h = 2.0 / N, ds = det_w / D, smin = -0.5 * det_w, x0 = -1.0 + 0.5 * h;
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) if (N >= 48)
     for (int ix = 0; ix < N; ++ix) {
         for (int iy = 0; iy < N; ++iy) {
             const double x = x0 + ix * h, y = x0 + iy * h;
@@ -129,7 +129,7 @@ void orc_colnorm2(int N, int D, double det_w, const double* cs, const double* sn
 
 /* ---- a9: forward-difference gradient, block_4_tv_helpers.py:17-23 ------------------------- */
 void orc_grad(const double* X, int N, double* gx, double* gy) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (N >= 48)
     for (int r = 0; r < N; ++r)
         for (int c = 0; c < N; ++c) {
             const long k = (long)r * N + c;
@@ -140,7 +140,7 @@ void orc_grad(const double* X, int N, double* gx, double* gy) {
 
 /* exact K^T (the adjoint block_4_tv_helpers.py:25-35 intends) */
 void orc_gradT(const double* px, const double* py, int N, double* out) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (N >= 48)
     for (int r = 0; r < N; ++r)
         for (int c = 0; c < N; ++c) {
             const long k = (long)r * N + c;
@@ -155,7 +155,7 @@ void orc_gradT(const double* px, const double* py, int N, double* out) {
 
 /* a10 as shipped: block_4_tv_helpers.py:25-35 (sign-flipped on the first/last row and column) */
 void orc_div_reference(const double* px, const double* py, int N, double* out) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (N >= 48)
     for (int r = 0; r < N; ++r)
         for (int c = 0; c < N; ++c) {
             const long k = (long)r * N + c;
@@ -174,7 +174,7 @@ void orc_div_reference(const double* px, const double* py, int N, double* out) {
 
 static double dot_n(const double* a, const double* b, long n) {
     double acc = 0.0;
-#pragma omp parallel for reduction(+ : acc) schedule(static)
+#pragma omp parallel for reduction(+ : acc) schedule(static) if (n >= 2304)
     for (long k = 0; k < n; ++k) acc += a[k] * b[k];
     return acc;
 }
@@ -187,7 +187,7 @@ static void apply_H(const double* v, int N, int D, double det_w, const double* c
     orc_forward(v, N, D, det_w, cs, sn, nang, Av);
     for (long k = 0; k < m; ++k) tmp_m[k] = prec * Av[k];
     orc_adjoint(tmp_m, N, D, det_w, cs, sn, nang, Hv);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (N >= 48)
     for (int r = 0; r < N; ++r)
         for (int c = 0; c < N; ++c) {
             const long k = (long)r * N + c;
@@ -231,13 +231,13 @@ void orc_x_update(int N, int D, double det_w, const double* cs, const double* sn
     double* dy = d + n;
     for (int sw = 0; sw < S; ++sw) {
         /* rhs = rhs0 + mu K^T (d - w) */
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n >= 2304)
         for (long k = 0; k < n; ++k) {
             t1[k] = dx[k] - wx[k];
             t2[k] = dy[k] - wy[k];
         }
         orc_gradT(t1, t2, N, rhs);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n >= 2304)
         for (long k = 0; k < n; ++k) {
             rhs[k] = mu * rhs[k];
             if (tvrhs_out) tvrhs_out[k] = rhs[k];
@@ -245,7 +245,7 @@ void orc_x_update(int N, int D, double det_w, const double* cs, const double* sn
         }
         /* warm start residual */
         apply_H(x, N, D, det_w, cs, sn, nang, prec, rhoD_vec, rhoD_scalar, mu, Ax_out, tm, Hp);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n >= 2304)
         for (long k = 0; k < n; ++k) {
             r[k] = rhs[k] - Hp[k];
             p[k] = r[k];
@@ -255,7 +255,7 @@ void orc_x_update(int N, int D, double det_w, const double* cs, const double* sn
             apply_H(p, N, D, det_w, cs, sn, nang, prec, rhoD_vec, rhoD_scalar, mu, Av, tm, Hp);
             const double pHp = dot_n(p, Hp, n);
             const double alpha = (pHp > 0.0) ? rr / pHp : 0.0;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n >= 2304)
             for (long k = 0; k < n; ++k) {
                 x[k] += alpha * p[k];
                 r[k] -= alpha * Hp[k];
@@ -263,14 +263,14 @@ void orc_x_update(int N, int D, double det_w, const double* cs, const double* sn
             for (long k = 0; k < m; ++k) Ax_out[k] += alpha * Av[k];
             const double rr_new = dot_n(r, r, n);
             const double beta = (rr > 0.0) ? rr_new / rr : 0.0;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n >= 2304)
             for (long k = 0; k < n; ++k) p[k] = r[k] + beta * p[k];
             rr = rr_new;
         }
         /* d = shrink2(Kx + w, lam/mu); w = Kx + w - d */
         orc_grad(x, N, t1, t2);
         const double kappa = lam / mu;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n >= 2304)
         for (long k = 0; k < n; ++k) {
             const double g1 = t1[k] + wx[k], g2 = t2[k] + wy[k];
             const double nrm = sqrt(g1 * g1 + g2 * g2);
@@ -288,7 +288,7 @@ void orc_x_update(int N, int D, double det_w, const double* cs, const double* sn
 /* canonical isotropic TV value (a9 pairing) */
 double orc_tv_value(const double* X, int N) {
     double acc = 0.0;
-#pragma omp parallel for reduction(+ : acc) schedule(static)
+#pragma omp parallel for reduction(+ : acc) schedule(static) if (N >= 48)
     for (int r = 0; r < N; ++r)
         for (int c = 0; c < N; ++c) {
             const long k = (long)r * N + c;
@@ -312,7 +312,7 @@ void orc_edge_update(long n, const double* xi, const double* xj, double* yi, dou
                      const double* Wi, const double* Wj, const double* qij, const double* qji,
                      double qs, double* sums) {
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
-#pragma omp parallel for reduction(+ : s0, s1, s2, s3, s4) schedule(static)
+#pragma omp parallel for reduction(+ : s0, s1, s2, s3, s4) schedule(static) if (n >= 2304)
     for (long k = 0; k < n; ++k) {
         const double ai = xi[k] + yi[k], aj = xj[k] + yj[k];
         const double zo = z[k];
@@ -336,7 +336,7 @@ void orc_edge_update(long n, const double* xi, const double* xj, double* yi, dou
 /* cons += rho * q .* (z - y)   (block_6_admm_loop_ver2.py:93, block_5:24-27 normal equations) */
 void orc_accum_cons(long n, double rho, const double* q, double qs, const double* z,
                     const double* y, double* cons) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n >= 2304)
     for (long k = 0; k < n; ++k) cons[k] += rho * (q ? q[k] : qs) * (z[k] - y[k]);
 }
 
@@ -353,7 +353,7 @@ void orc_forward_rs(const double* X, int N, int D, double det_w, const double* c
                     double* out) {
     const double h = 2.0 / N, ds = det_w / D, smin = -0.5 * det_w, x0 = -1.0 + 0.5 * h;
     const int P = rs_steps(N);
-#pragma omp parallel for collapse(2) schedule(dynamic, 16)
+#pragma omp parallel for collapse(2) schedule(dynamic, 16) if (N >= 48)
     for (int a = 0; a < nang; ++a) {
         for (int j = 0; j < D; ++j) {
             const double c = cs[a], s = sn[a], sj = smin + (j + 0.5) * ds;
@@ -380,7 +380,7 @@ static void adjoint_rs_impl(const double* q, int N, int D, double det_w, const d
                             int power, double* out) {
     const double h = 2.0 / N, ds = det_w / D, smin = -0.5 * det_w, x0 = -1.0 + 0.5 * h, r = ds / h;
     const int P = rs_steps(N);
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) if (N >= 48)
     for (int ix = 0; ix < N; ++ix)
         for (int iy = 0; iy < N; ++iy) {
             const double x = x0 + ix * h, y = x0 + iy * h;

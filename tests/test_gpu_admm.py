@@ -61,16 +61,21 @@ def _compare(hg, ho, xg, xo, img, N, iters, report=None):
 
 
 def test_ring_uniform_q_200_iterations():
-    """BASELINE cfg-1 shape (ring of 4, uniform Q, lam 0.02, rho 2) at N=64, 200 outer iterations."""
+    """BASELINE cfg-1 shape (ring of 4, uniform Q, lam 0.02, rho 2) at N=64, 200 outer iterations, one 1 x 8 solve per
+    iteration (round 1's schedule).  With the a14 rule on top (3 x 8 CG per iteration) this small problem converges to
+    fp32 resolution well before iteration 200 -- |x_i - z| falls to ~1e-4 |x|, where the 6e-8 rounding of x and z alone
+    moves the primal trace by ~1e-3 -- so the 200-iteration run with the rule is made at cfg 1's real size below."""
     from block_6_admm_loop_ver2 import decentralized_admm
     from oracle import oracle as O
     N, M, V, iters = 64, 180, 4, 200
     thetas, img, ops_o, ops_g, sinos = _problem(N, M, V)
     G = O.make_graph("ring", V)
     kw = dict(lam_tv=0.02, rho=2.0, max_iters=iters, eps_pri=0.0, eps_dual=0.0, phantom_true=img)
-    xo, ho = O.decentralized_admm(ops_o, sinos, G, None, None, N, uniform_q=1.0, tv_sweeps=1, cg_iters=8, **kw)
-    xg, hg = decentralized_admm(ops_g, sinos, G, None, None, N, verbose=False, cg_iters=8, tv_sweeps=1, **kw)
-    _compare(hg, ho, xg, xo, img, N, iters)
+    xo, ho = O.decentralized_admm(ops_o, sinos, G, None, None, N, uniform_q=1.0, tv_sweeps=1, cg_iters=8,
+                                  acceptance=False, **kw)
+    xg, hg = decentralized_admm(ops_g, sinos, G, None, None, N, verbose=False, cg_iters=8, tv_sweeps=1,
+                                acceptance=False, **kw)
+    _compare(hg, ho, xg, xo, img, N, iters, report="ring4 64^2 x200 (1x8, no rule)")
     assert np.stack(xg).shape == (V, N * N)
 
 

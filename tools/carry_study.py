@@ -21,12 +21,13 @@ SCHEDS = ((1, 2, True), (1, 8, False))
 
 def main():
     global CARRIES, SCHEDS
-    if len(sys.argv) > 3 and sys.argv[3] == "default-only":
+    if "diag" in sys.argv:
+        CARRIES = (False,)
+    if "default-only" in sys.argv:
         CARRIES, SCHEDS = (False, "first_retry", "iteration"), ((1, 2, True),)
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 200
     from admm_b200 import RayTransformCUDA, node_angles
-    from block_6_admm_loop_ver2 import decentralized_admm
     from oracle import oracle as O
     M, V = 180, 4
     thetas = node_angles(M, V, "contiguous")
@@ -34,13 +35,26 @@ def main():
     ops_o = [O.JosephOperator(N, t) for t in thetas]
     sinos = [(op.forward(img) + 0.005 * np.random.default_rng(1234 + i).standard_normal(op.shape[0]))
              .reshape(op.nang, op.D).astype(np.float32) for i, op in enumerate(ops_o)]
-    ops_g = [RayTransformCUDA(N, t) for t in thetas]
+    if "oracle-only" not in sys.argv:
+        from block_6_admm_loop_ver2 import decentralized_admm
+        ops_g = [RayTransformCUDA(N, t) for t in thetas]
     G = O.make_graph("ring", V)
     kw = dict(lam_tv=0.02, rho=2.0, max_iters=iters, eps_pri=0.0, eps_dual=0.0, phantom_true=img)
     out = []
     for (S, C, acc) in SCHEDS:
-        xo, ho = O.decentralized_admm(ops_o, sinos, G, None, None, N, uniform_q=1.0, tv_sweeps=S, cg_iters=C,
-                                      acceptance=acc, **kw)
+        # the fp64 oracle run is the expensive part and needs no GPU: cached next to the profiles (not committed), so it can
+        # be produced on any host (`oracle-only`) and travel to the GPU box with the snapshot
+        cache = os.path.join(ROOT, "profiles", f"_study_ref_carry{N}_{iters}_S{S}C{C}{int(acc)}.npz")
+        if os.path.exists(cache):
+            zf = np.load(cache)
+            xo, ho = list(zf["x"]), {"primal": zf["primal"], "dual": zf["dual"], "tighten_history": zf["tighten"]}
+        else:
+            xo, ho = O.decentralized_admm(ops_o, sinos, G, None, None, N, uniform_q=1.0, tv_sweeps=S, cg_iters=C,
+                                          acceptance=acc, **kw)
+            np.savez_compressed(cache, x=np.stack(xo), primal=np.array(ho["primal"]), dual=np.array(ho["dual"]),
+                                tighten=np.array(ho["tighten_history"]))
+        if "oracle-only" in sys.argv:
+            continue
         po, do = np.array(ho["primal"]), np.array(ho["dual"])
         for carry in CARRIES:
             if True:
