@@ -2,6 +2,7 @@
 // (consensus z / dual y / residual) kernel, K6 right-hand-side assembly, and the small per-iteration
 // bookkeeping kernels.  sm_100a.  All are single-pass streaming kernels (HBM-bound).
 #include <cstdlib>
+#include <mutex>
 
 #include "solver_kernels.cuh"
 
@@ -235,15 +236,174 @@ __device__ __forceinline__ void tv_quad(const TvParams& P, const float* __restri
 // rotate through registers (one new x row per step).  Per pixel the operations and their order are those of tv_quad<true>: results are bit-identical.
 constexpr int TVROWS = 8;
 
+template <int PX> struct VecPx;
+template <> struct VecPx<4> {
+    static __device__ __forceinline__ void ld(const float* p, float* o) { const float4 v = ld4(p); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+    static __device__ __forceinline__ void st(float* p, const float* v) { st4(p, make_float4(v[0], v[1], v[2], v[3])); }
+};
+template <> struct VecPx<2> {
+    static __device__ __forceinline__ void ld(const float* p, float* o) { const float2 v = *reinterpret_cast<const float2*>(p); o[0] = v.x; o[1] = v.y; }
+    static __device__ __forceinline__ void st(float* p, const float* v) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+
+// PX = pixels per thread and row (4: float4 accesses, 80 registers; 2: float2 accesses, half the per-thread state -> twice
+// the resident warps, at one more left-neighbour evaluation per 4 pixels)
+template <int PX>
 __device__ __forceinline__ void tv_strip(const TvParams& P, const float* __restrict__ x, const float* __restrict__ w1p,
                                          const float* __restrict__ w2p, float* __restrict__ wo1, float* __restrict__ wo2,
                                          long long nb, int N, int r0, int c0, float kappa, float alpha, float& tv, float& gn2,
                                          float& img, float& rr) {
+    typedef VecPx<PX> V;
     const bool diag = (P.r != nullptr);
     const bool upd = (P.r_upd != nullptr);
     const float* rsrc = P.r ? P.r : P.r_upd;    // read where the CG left r; the carried one is written to r_upd
     float* __restrict__ tvt = P.tvterm + nb;
     long long g0 = (long long)r0 * N + c0;
+    // prologue: rows r0 - 1 and r0, and the upper-neighbour values of row r0
+    float xm[PX], xc[PX + 2], dwx_up[PX], px_up[PX];
+    {
+        float xm5[PX + 1], wu1[PX], wu2[PX];
+        V::ld(x + g0 - N, xm5);
+        xm5[PX] = x[g0 - N + PX];
+        V::ld(x + g0, xc + 1);
+        xc[0] = x[g0 - 1];
+        xc[PX + 1] = x[g0 + PX];
+        V::ld(w1p + g0 - N, wu1);
+        V::ld(w2p + g0 - N, wu2);
+#pragma unroll
+        for (int k = 0; k < PX; ++k) {
+            xm[k] = xm5[k];
+            const float gxu = xc[k + 1] - xm5[k], gyu = xm5[k + 1] - xm5[k];
+            dwx_up[k] = shrink_dw(gxu, gyu, wu1[k], wu2[k], kappa).dwx;
+            float pyu, mg;
+            unit_grad(gxu, gyu, px_up[k], pyu, mg);
+        }
+    }
+#pragma unroll 1
+    for (int i = 0; i < TVROWS; ++i, g0 += N) {
+        // loads of one row: x of the row below (c0-1 .. c0+PX), w (c0-1 .. c0+PX-1), tvterm, r (- alpha Hp), x_true
+        float xp[PX + 2], wc1[PX + 1], wc2[PX + 1], told[PX], rc[PX], xt[PX];
+        V::ld(x + g0 + N, xp + 1);
+        xp[0] = x[g0 + N - 1];
+        xp[PX + 1] = x[g0 + N + PX];
+        V::ld(w1p + g0, wc1 + 1);
+        V::ld(w2p + g0, wc2 + 1);
+        wc1[0] = w1p[g0 - 1];
+        wc2[0] = w2p[g0 - 1];
+        V::ld(tvt + g0, told);
+#pragma unroll
+        for (int k = 0; k < PX; ++k) { rc[k] = 0.f; xt[k] = 0.f; }
+        if (diag || upd) {
+            V::ld(rsrc + nb + g0, rc);
+            if (P.hp) {      // the pending half of the last CG update: r <- r - alpha Hp
+                float h[PX];
+                V::ld(P.hp + nb + g0, h);
+#pragma unroll
+                for (int k = 0; k < PX; ++k) rc[k] = fmaf(-alpha, h[k], rc[k]);
+            }
+        }
+        if (P.xtrue) V::ld(P.xtrue + g0, xt);
+        float dwy_prev, py_prev;
+        {
+            const float gx = xp[0] - xc[0], gy = xc[1] - xc[0];
+            dwy_prev = shrink_dw(gx, gy, wc1[0], wc2[0], kappa).dwy;
+            float pxl, mg;
+            unit_grad(gx, gy, pxl, py_prev, mg);
+        }
+        float w1o[PX], w2o[PX], tvo[PX];
+#pragma unroll
+        for (int k = 0; k < PX; ++k) {
+            const float xcv = xc[k + 1];
+            const float gx = xp[k + 1] - xcv, gy = xc[k + 2] - xcv;
+            const Dw o = shrink_dw(gx, gy, wc1[k + 1], wc2[k + 1], kappa);
+            float kt = dwx_up[k];
+            kt -= o.dwx;
+            kt += dwy_prev;
+            kt -= o.dwy;
+            float pxo, pyo, mag;
+            unit_grad(gx, gy, pxo, pyo, mag);
+            tv += mag;
+            if (diag) {
+                float lap = 0.f;
+                lap += xcv - xm[k];
+                lap += xcv - xp[k + 1];
+                lap += xcv - xc[k];
+                lap += xcv - xc[k + 2];
+                float dv = 0.f;
+                dv += px_up[k] - pxo;
+                dv += py_prev - pyo;
+                const float gv = told[k] - rc[k] - P.mu * lap + P.lam * dv;
+                gn2 = fmaf(gv, gv, gn2);
+            }
+            if (P.xtrue) { const float e = xcv - xt[k]; img = fmaf(e, e, img); }
+            w1o[k] = o.w1; w2o[k] = o.w2; tvo[k] = P.mu * kt;
+            dwy_prev = o.dwy; py_prev = pyo;
+            dwx_up[k] = o.dwx; px_up[k] = pxo;      // the row below sees this row as its upper neighbour
+        }
+        V::st(wo1 + g0, w1o);
+        V::st(wo2 + g0, w2o);
+        V::st(tvt + g0, tvo);
+        if (upd) {
+            float rn[PX];
+#pragma unroll
+            for (int k = 0; k < PX; ++k) { rn[k] = rc[k] + (tvo[k] - told[k]); rr = fmaf(rn[k], rn[k], rr); }
+            V::st(P.r_upd + nb + g0, rn);
+            if (P.p_out) V::st(P.p_out + nb + g0, rn);
+        }
+#pragma unroll
+        for (int k = 0; k < PX; ++k) xm[k] = xc[k + 1];
+#pragma unroll
+        for (int k = 0; k < PX + 2; ++k) xc[k] = xp[k];
+    }
+}
+
+// ---- the same march with the NEXT row's operands in flight: every thread copies them global -> shared with cp.async
+// (LDGSTS: no registers held while they travel) into its own slots of a double buffer and reads them back when the row's
+// turn comes; nothing is shared between threads, so no barrier is involved.  8 slots of 16 bytes per thread and buffer:
+// x(row+1), w1, w2, tvterm, r, Hp, x_true, {x(row+1)[c0-1], x(row+1)[c0+4], w1[c0-1], w2[c0-1]}.
+constexpr int TVSLOTS = 8;
+constexpr size_t kTvAsyncSmem = (size_t)2 * TVSLOTS * TVX * TVY * 16;
+
+__device__ __forceinline__ void cp_async16(unsigned dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NLEFT>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NLEFT) : "memory"); }
+
+__device__ __forceinline__ void tv_strip_async(const TvParams& P, const float* __restrict__ x, const float* __restrict__ w1p,
+                                               const float* __restrict__ w2p, float* __restrict__ wo1,
+                                               float* __restrict__ wo2, long long nb, int N, int r0, int c0, float kappa,
+                                               float alpha, unsigned char* smem, float& tv, float& gn2, float& img, float& rr) {
+    const bool diag = (P.r != nullptr);
+    const bool upd = (P.r_upd != nullptr);
+    const bool need_r = diag || upd;
+    const float* rsrc = P.r ? P.r : P.r_upd;
+    float* __restrict__ tvt = P.tvterm + nb;
+    long long g0 = (long long)r0 * N + c0;
+    const int tid = threadIdx.y * TVX + threadIdx.x;
+    const unsigned sbase = smem_u32(smem) + (unsigned)tid * 16u;
+    const float4* sv = reinterpret_cast<const float4*>(smem) + tid;
+    constexpr unsigned SLOT = TVX * TVY * 16, BUF = TVSLOTS * SLOT;   // bytes
+    auto issue = [&](long long g, int buf) {
+        const unsigned d = sbase + (unsigned)buf * BUF;
+        cp_async16(d + 0 * SLOT, x + g + N);
+        cp_async16(d + 1 * SLOT, w1p + g);
+        cp_async16(d + 2 * SLOT, w2p + g);
+        cp_async16(d + 3 * SLOT, tvt + g);
+        if (need_r) cp_async16(d + 4 * SLOT, rsrc + nb + g);
+        if (need_r && P.hp) cp_async16(d + 5 * SLOT, P.hp + nb + g);
+        if (P.xtrue) cp_async16(d + 6 * SLOT, P.xtrue + g);
+        cp_async4(d + 7 * SLOT + 0, x + g + N - 1);
+        cp_async4(d + 7 * SLOT + 4, x + g + N + 4);
+        cp_async4(d + 7 * SLOT + 8, w1p + g - 1);
+        cp_async4(d + 7 * SLOT + 12, w2p + g - 1);
+        cp_async_commit();
+    };
+    issue(g0, 0);
     // prologue: rows r0 - 1 and r0, and the upper-neighbour values of row r0
     float xm[4], xc[6], dwx_up[4], px_up[4];
     {
@@ -262,32 +422,27 @@ __device__ __forceinline__ void tv_strip(const TvParams& P, const float* __restr
             unit_grad(gxu, gyu, px_up[k], pyu, mg);
         }
     }
-    // loads of one row: x of the row below (c0-1 .. c0+4), w (c0-1 .. c0+3), tvterm, r, x_true
-    struct Row { float4 xp, w1, w2; float xpl, xpr, w1l, w2l; };
-    auto load_row = [&](long long g) {
-        Row R;
-        R.xp = ld4(x + g + N); R.xpl = x[g + N - 1]; R.xpr = x[g + N + 4];
-        R.w1 = ld4(w1p + g); R.w2 = ld4(w2p + g); R.w1l = w1p[g - 1]; R.w2l = w2p[g - 1];
-        return R;
-    };
 #pragma unroll 1
     for (int i = 0; i < TVROWS; ++i, g0 += N) {
-        const Row cur = load_row(g0);
-        // consumed at the end of the per-pixel arithmetic: issued here, no extra registers across iterations
-        const float4 t4 = ld4(tvt + g0);
+        const int buf = i & 1;
+        if (i + 1 < TVROWS) { issue(g0 + N, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        const float4* b = sv + buf * (TVSLOTS * TVX * TVY);
+        const float4 xq = b[0 * TVX * TVY], w1q = b[1 * TVX * TVY], w2q = b[2 * TVX * TVY], t4 = b[3 * TVX * TVY];
+        const float4 sc4 = b[7 * TVX * TVY];
         float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f), x4 = r4;
-        if (diag || upd) {
-            r4 = ld4(rsrc + nb + g0);
-            if (P.hp) {
-                const float4 h4 = ld4(P.hp + nb + g0);
+        if (need_r) {
+            r4 = b[4 * TVX * TVY];
+            if (P.hp) {      // the pending half of the last CG update: r <- r - alpha Hp
+                const float4 h4 = b[5 * TVX * TVY];
                 r4.x = fmaf(-alpha, h4.x, r4.x); r4.y = fmaf(-alpha, h4.y, r4.y);
                 r4.z = fmaf(-alpha, h4.z, r4.z); r4.w = fmaf(-alpha, h4.w, r4.w);
             }
         }
-        if (P.xtrue) x4 = ld4(P.xtrue + g0);
-        const float xp[6] = {cur.xpl, cur.xp.x, cur.xp.y, cur.xp.z, cur.xp.w, cur.xpr};
-        const float wc1[5] = {cur.w1l, cur.w1.x, cur.w1.y, cur.w1.z, cur.w1.w};
-        const float wc2[5] = {cur.w2l, cur.w2.x, cur.w2.y, cur.w2.z, cur.w2.w};
+        if (P.xtrue) x4 = b[6 * TVX * TVY];
+        const float xp[6] = {sc4.x, xq.x, xq.y, xq.z, xq.w, sc4.y};
+        const float wc1[5] = {sc4.z, w1q.x, w1q.y, w1q.z, w1q.w};
+        const float wc2[5] = {sc4.w, w2q.x, w2q.y, w2q.z, w2q.w};
         const float told[4] = {t4.x, t4.y, t4.z, t4.w};
         const float rc[4] = {r4.x, r4.y, r4.z, r4.w};
         const float xt[4] = {x4.x, x4.y, x4.z, x4.w};
@@ -326,7 +481,7 @@ __device__ __forceinline__ void tv_strip(const TvParams& P, const float* __restr
             if (P.xtrue) { const float e = xcv - xt[k]; img = fmaf(e, e, img); }
             w1o[k] = o.w1; w2o[k] = o.w2; tvo[k] = P.mu * kt;
             dwy_prev = o.dwy; py_prev = pyo;
-            dwx_up[k] = o.dwx; px_up[k] = pxo;      // the row below sees this row as its upper neighbour
+            dwx_up[k] = o.dwx; px_up[k] = pxo;
         }
         st4(wo1 + g0, make_float4(w1o[0], w1o[1], w1o[2], w1o[3]));
         st4(wo2 + g0, make_float4(w2o[0], w2o[1], w2o[2], w2o[3]));
@@ -345,7 +500,8 @@ __device__ __forceinline__ void tv_strip(const TvParams& P, const float* __restr
     }
 }
 
-__global__ void __launch_bounds__(TVX * TVY, 3)
+template <int PX>
+__global__ void __launch_bounds__(TVX * TVY, PX == 4 ? 3 : 4)
 tv_fused_kernel(const TvParams P) {
     __shared__ __align__(16) float red[128];
     const int N = P.N;
@@ -354,7 +510,7 @@ tv_fused_kernel(const TvParams P) {
     const long long nb = (long long)blockIdx.z * P.stride;
     const long long n = (long long)N * N;
     const int r0 = (blockIdx.y * TVY + threadIdx.y) * TVROWS;   // first of this thread's TVROWS rows
-    const int c0 = (blockIdx.x * TVX + threadIdx.x) * 4;
+    const int c0 = (blockIdx.x * TVX + threadIdx.x) * PX;
     const float* __restrict__ x = P.x + nb;
     // device-side ping-pong parity of this node's multiplier (host parity when there is no control table): every block
     // reads it before it arrives at the grid-reduction counter, the last block flips it after all have arrived
@@ -368,11 +524,17 @@ tv_fused_kernel(const TvParams P) {
     float tv = 0.f, gn2 = 0.f, img = 0.f, rr = 0.f;
     // block-uniform: rows [by*TVY*TVROWS, +TVY*TVROWS) and columns [bx*4*TVX, +4*TVX) all strictly inside the image
     const bool interior = ((N & 3) == 0) && blockIdx.y >= 1 && (int)(blockIdx.y + 1) * TVY * TVROWS <= N - 1 &&
-                          blockIdx.x >= 1 && (int)(blockIdx.x + 1) * 4 * TVX <= N - 1;
-    if (interior && P.strip) tv_strip(P, x, w1p, w2p, wo1, wo2, nb, N, r0, c0, kappa, alpha, tv, gn2, img, rr);
+                          blockIdx.x >= 1 && (int)(blockIdx.x + 1) * PX * TVX <= N - 1;
+    // the per-row forms work on quads: with PX = 2 every other thread takes one
+    const bool quad = (PX == 4) || ((threadIdx.x & 1) == 0);
+    extern __shared__ __align__(16) unsigned char tv_smem[];
+    if (PX == 4 && interior && P.strip == 2)
+        tv_strip_async(P, x, w1p, w2p, wo1, wo2, nb, N, r0, c0, kappa, alpha, tv_smem, tv, gn2, img, rr);
+    else if (interior && P.strip) tv_strip<PX>(P, x, w1p, w2p, wo1, wo2, nb, N, r0, c0, kappa, alpha, tv, gn2, img, rr);
     else if (interior) {
-        for (int r = r0; r < r0 + TVROWS; ++r) tv_quad<true>(P, x, w1p, w2p, wo1, wo2, nb, N, r, c0, kappa, alpha, tv, gn2, img, rr);
-    } else if (c0 < N) {
+        if (quad)
+            for (int r = r0; r < r0 + TVROWS; ++r) tv_quad<true>(P, x, w1p, w2p, wo1, wo2, nb, N, r, c0, kappa, alpha, tv, gn2, img, rr);
+    } else if (quad && c0 < N) {
         for (int r = r0; r < min(r0 + TVROWS, N); ++r) tv_quad<false>(P, x, w1p, w2p, wo1, wo2, nb, N, r, c0, kappa, alpha, tv, gn2, img, rr);
     }
     float v[4] = {tv, gn2, img, rr};
@@ -778,11 +940,33 @@ static inline int stream_blocks(long long n, int per_thread) {
 }
 
 cudaError_t launch_tv(const TvParams& P0, int nodes, cudaStream_t st) {
-    static const int strip = [] { const char* e = getenv("ADMM_B200_TVSTRIP"); return (e && e[0] == '0') ? 0 : 1; }();
+    // ADMM_B200_TVSTRIP: 0 per-row form, 1 row march with register loads, 2 (default) row march with cp.async staging
+    static const int strip = [] { const char* e = getenv("ADMM_B200_TVSTRIP"); return e ? atoi(e) : 2; }();
     TvParams P = P0;
     P.strip = strip;
-    dim3 grid((P.N + 4 * TVX - 1) / (4 * TVX), (P.N + TVY * TVROWS - 1) / (TVY * TVROWS), nodes);
-    { ProfScope ps(KC_TV, st); tv_fused_kernel<<<grid, dim3(TVX, TVY), 0, st>>>(P); }
+    // pixels per thread and row: 2 for large images (twice the resident warps), 4 otherwise; ADMM_B200_TVPX overrides
+    static const int px_env = [] { const char* e = getenv("ADMM_B200_TVPX"); return e ? atoi(e) : 0; }();
+    const int px = (px_env == 2 || px_env == 4) ? px_env : 4;
+    dim3 grid((P.N + px * TVX - 1) / (px * TVX), (P.N + TVY * TVROWS - 1) / (TVY * TVROWS), nodes);
+    size_t smem = 0;
+    if (px == 4 && P.strip == 2) {
+        // the dynamic shared-memory limit is a per-device function attribute
+        static std::mutex mu;
+        static bool done[64] = {false};
+        std::lock_guard<std::mutex> lk(mu);
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= 64 || !done[dev]) {
+            e = cudaFuncSetAttribute(tv_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTvAsyncSmem);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
+        smem = kTvAsyncSmem;
+    }
+    ProfScope ps(KC_TV, st);
+    if (px == 2) tv_fused_kernel<2><<<grid, dim3(TVX, TVY), 0, st>>>(P);
+    else tv_fused_kernel<4><<<grid, dim3(TVX, TVY), smem, st>>>(P);
     return cudaGetLastError();
 }
 cudaError_t launch_cg_update(const CgParams& P, int nodes, int nblk, cudaStream_t st) {

@@ -1,7 +1,7 @@
 # run one gpurun command, retrying while the pod answers "no slot" (exit 3, nothing charged)
-# usage: tools/gpu_retry.sh <timeout-seconds> '<command>'
+# usage: [GPUS=N] tools/gpu_retry.sh <timeout-seconds> '<command>'
 for i in $(seq 1 20); do
-  /usr/local/graft/bin/gpurun --timeout "$1" -- "$2"; rc=$?
+  /usr/local/graft/bin/gpurun ${GPUS:+--gpus $GPUS} --timeout "$1" -- "$2"; rc=$?
   if [ $rc -ne 3 ]; then break; fi
   sleep 90
 done
