@@ -269,6 +269,38 @@ def test_cfg1_full_size_200_iterations():
             assert t.max() == 2 and t.min() >= 0 and t[0].max() < 2
 
 
+def test_cfg1_full_size_200_iterations_default_schedule():
+    """cfg 1 at its real size with the DEFAULT schedule of the bench and of decentralized_admm -- 1 sweep x 2 CG per
+    solve, the a14 rule on (3 solves per node and iteration), the CG residual carried between the solves of an iteration
+    -- for 200 iterations, against the fp64 oracle's run of the same problem.  The oracle run (2 minutes of host time)
+    is a committed fixture: tests/golden/cfg1_default_schedule_200.npz, written by
+    `python tools/carry_study.py 128 200 default-only oracle-only` (oracle.decentralized_admm, same seeds as _problem)."""
+    import os
+    from block_6_admm_loop_ver2 import decentralized_admm
+    from oracle import oracle as O
+    N, M, V, iters = 128, 180, 4, 200
+    thetas, img, ops_o, ops_g, sinos = _problem(N, M, V)
+    G = O.make_graph("ring", V)
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg1_default_schedule_200.npz"))
+    # the fixture belongs to these inputs: the oracle's first iteration reproduces its first trace entries
+    x1, h1 = O.decentralized_admm(ops_o, sinos, G, None, None, N, uniform_q=1.0, lam_tv=0.02, rho=2.0, max_iters=2,
+                                  eps_pri=0.0, eps_dual=0.0, phantom_true=img, tv_sweeps=1, cg_iters=2, acceptance=True)
+    assert np.allclose(h1["primal"], ref["primal"][:2], rtol=1e-9) and np.allclose(h1["dual"], ref["dual"][:2], rtol=1e-9)
+    xg, hg = decentralized_admm(ops_g, sinos, G, None, None, N, verbose=False, lam_tv=0.02, rho=2.0, max_iters=iters,
+                                eps_pri=0.0, eps_dual=0.0, phantom_true=img)      # every solver control at its default
+    pg, dg = np.array(hg["primal"]), np.array(hg["dual"])
+    err = {"primal": float(np.max(np.abs(pg - ref["primal"]) / ref["primal"])),
+           "dual": float(np.max(np.abs(dg - ref["dual"]) / ref["dual"])),
+           "x": float(max(np.linalg.norm(xg[i] - ref["x"][i]) / np.linalg.norm(ref["x"][i]) for i in range(V))),
+           "psnr_db": float(max(abs(O.psnr(xg[i].reshape(N, N), img) - O.psnr(ref["x"][i].reshape(N, N), img))
+                                for i in range(V)))}
+    print("PARITY cfg1 128^2 x200 default schedule (S1 C2 + rule, carried residual): " +
+          ", ".join(f"{k} {v:.2e}" for k, v in err.items()))
+    assert np.array_equal(np.array(hg["tighten_history"]), ref["tighten"])
+    assert err["primal"] < TRACE_TOL and err["dual"] < TRACE_TOL, err
+    assert err["x"] < RECON_TOL and err["psnr_db"] < PSNR_TOL, err
+
+
 def _cfg_problem_gpu_sinos(N, M, V, hetero):
     """Inputs of the large configs: b_i = A_i x_true + sigma_i eps_i with A_i x_true from the fp64 oracle."""
     return _problem(N, M, V, hetero=hetero)

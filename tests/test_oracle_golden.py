@@ -113,3 +113,22 @@ def test_outer_loop_matches_reference_block6(tag):
                                   eps_dual=1e-9, phantom_true=O.shepp_logan(N), tv_mu=mu, tv_sweeps=S, cg_iters=C)
     assert np.allclose(np.array(h2["primal"]), G[f"b6_{tag}_primal"], rtol=1e-5)
     assert np.allclose(np.array(h2["dual"]), G[f"b6_{tag}_dual"], rtol=1e-5)
+
+
+def test_cfg1_default_schedule_fixture_is_the_oracles():
+    """tests/golden/cfg1_default_schedule_200.npz (the 200-iteration fp64 run behind the GPU default-schedule parity test,
+    written by `tools/carry_study.py 128 200 default-only oracle-only`) starts like the oracle run of the same inputs."""
+    import os
+    N, M, V = 128, 180, 4
+    thetas = O.node_angles(M, V, "contiguous")
+    img = O.shepp_logan(N)
+    ops = [O.JosephOperator(N, t) for t in thetas]
+    sinos = [(op.forward(img) + 0.005 * np.random.default_rng(1234 + i).standard_normal(op.shape[0]))
+             .reshape(op.nang, op.D).astype(np.float32) for i, op in enumerate(ops)]
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg1_default_schedule_200.npz"))
+    x, h = O.decentralized_admm(ops, sinos, O.make_graph("ring", V), None, None, N, uniform_q=1.0, lam_tv=0.02, rho=2.0,
+                                max_iters=3, eps_pri=0.0, eps_dual=0.0, phantom_true=img, tv_sweeps=1, cg_iters=2,
+                                acceptance=True)
+    assert np.allclose(h["primal"], ref["primal"][:3], rtol=1e-9) and np.allclose(h["dual"], ref["dual"][:3], rtol=1e-9)
+    assert np.array_equal(np.array(h["tighten_history"]), ref["tighten"][:3])
+    assert ref["primal"].shape == (200,) and ref["x"].shape == (V, N * N)
