@@ -21,6 +21,10 @@ namespace admm {
 // register, then adds it to the block's per-angle accumulator row in shared memory (one owner per bin
 // per slab -> no atomics).  At the end the rows are stored as fixed-size records; fwd_reduce_kernel sums
 // the records of all strips/segments in a fixed order (deterministic) and applies the step weight.
+// TMA (tma.cuh): in a plain projection the y-dominant tile -- whose canonical layout is the image's own row-major
+// order -- lands by one cp.async.bulk.tensor.3d per slab (zero-filled outside the image, mbarrier arrival); while a slab
+// is sampled the next slab's boxes of every operand stream are prefetched to L2 (cp.async.bulk.prefetch.tensor).
+// x-dominant tiles (transposed on the way in) and the CG-fused mode (updated on the way in) are staged by the threads.
 // =================================================================================================
 __global__ void __launch_bounds__(FTHREADS, 4)
 fwd_strip_kernel(const __grid_constant__ FwdParams P) {
