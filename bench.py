@@ -464,8 +464,13 @@ def main():
     deg_sum = sum(G.degree(g) for g in eng.loc)
     alg = {  # algorithmic bytes per launch (this rank), DESIGN.md "Kernels"
         "fwd": 4 * (Vl * n + m_loc), "fwd_fused": 4 * ((7 if not args.no_fuse else 3) * Vl * n + m_loc),
-        "back_hp": 4 * (m_loc + (2 + nz) * Vl * n), "back_resid0": 4 * (m_loc + (5 + nz) * Vl * n),
-        "cg_update": 4 * 6 * Vl * n, "p_update": 4 * 3 * Vl * n, "tv": 4 * 9 * Vl * n,
+        # back_resid0: reads x, rhs0, tvterm, writes r (p0 = r is not materialised in the fused CG); cg_update: the x half of
+        # the solve's last update (reads x, p, writes x); tv: reads x, w (2), tvterm, r, Hp, writes w' (2), tvterm' and -- in
+        # the passes that hand the residual on (2 of 3 with the a14 rule and the carried residual) -- r
+        "back_hp": 4 * (m_loc + (2 + nz) * Vl * n),
+        "back_resid0": 4 * (m_loc + ((4 if not args.no_fuse else 5) + nz) * Vl * n),
+        "cg_update": 4 * (3 if not args.no_fuse else 6) * Vl * n, "p_update": 4 * 3 * Vl * n,
+        "tv": int(4 * (9 + (2.0 / 3.0 if (args.carry != "off" and args.acceptance) else 0.0)) * Vl * n),
         "rhs0": 4 * ((2 + nz) * deg_sum + 2 * Vl) * n, "edge": 4 * 8 * n * max(El, 1),
     }
     kernels = []
