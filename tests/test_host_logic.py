@@ -274,3 +274,23 @@ def test_block3_checker_invariants():
                 assert wsum[i, j] <= float(np.sum(np.minimum(Wi[i], Wi[j]))) + 1e-12
         assert count.sum() == 2 * np.triu(count, 1).sum()
         assert np.isclose(wsum.sum(), 2.0 * np.triu(wsum, 1).sum())
+
+
+def test_cfg4_node_to_gpu_maps_fixture():
+    """The default (angle-balanced min-cut) node -> GPU maps of BASELINE cfg 4 (64 nodes, ER p = 0.1, 720 angles) at 2, 4
+    and 8 GPUs are integer work: bit-exact against the committed maps (tests/golden/cfg4_node_maps.json), 64 / G nodes and
+    720 / G angle rows per rank."""
+    import json
+    from admm_b200 import make_graph
+    from admm_b200.sharding import cut_statistics, partition_nodes
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "cfg4_node_maps.json")))
+    G = make_graph("er", 64, seed=0, p=0.1)
+    assert G.number_of_edges() == fx["edges"] == 201
+    w = [len(t) for t in node_angles(720, 64)]
+    for world in (2, 4, 8):
+        m = fx["maps"][str(world)]
+        nr = partition_nodes(G, world, "auto", weights=w)
+        assert [int(v) for v in nr] == m["node_rank"]
+        assert cut_statistics(G, world, nr)["cut"] == m["cut_edges"]
+        assert [nr.count(r) for r in range(world)] == [64 // world] * world
+        assert [sum(w[i] for i in range(64) if nr[i] == r) for r in range(world)] == [720 // world] * world
