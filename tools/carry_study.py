@@ -57,21 +57,20 @@ def main():
             continue
         po, do = np.array(ho["primal"]), np.array(ho["dual"])
         for carry in CARRIES:
-            if True:
-                xg, hg = decentralized_admm(ops_g, sinos, G, None, None, N, verbose=False, tv_sweeps=S, cg_iters=C,
-                                            acceptance=acc, carry_residual=carry, **kw)
-                pg, dg = np.array(hg["primal"]), np.array(hg["dual"])
-                ep, ed = np.abs(pg - po) / po, np.abs(dg - do) / do
-                xe = max(np.linalg.norm(a - b) / np.linalg.norm(b) for a, b in zip(xg, xo))
-                row = {"N": N, "S": S, "C": C, "accept": acc, "carry": carry, "primal_max": float(ep.max()),
-                       "primal_argmax": int(ep.argmax()), "dual_max": float(ed.max()), "dual_argmax": int(ed.argmax()),
-                       "x": float(xe), "primal_at": {k: float(ep[k - 1]) for k in (10, 50, 100, iters) if k <= iters},
-                       "dual_at": {k: float(ed[k - 1]) for k in (10, 50, 100, iters) if k <= iters},
-                       "primal_last": float(po[-1]), "dual_last": float(do[-1]),
-                       "same_decisions": bool(np.array_equal(np.array(hg["tighten_history"]),
-                                                             np.array(ho["tighten_history"])))}
-                print(json.dumps(row), flush=True)
-                out.append(row)
+            xg, hg = decentralized_admm(ops_g, sinos, G, None, None, N, verbose=False, tv_sweeps=S, cg_iters=C,
+                                        acceptance=acc, carry_residual=carry, **kw)
+            pg, dg = np.array(hg["primal"]), np.array(hg["dual"])
+            ep, ed = np.abs(pg - po) / po, np.abs(dg - do) / do
+            xe = max(np.linalg.norm(a - b) / np.linalg.norm(b) for a, b in zip(xg, xo))
+            row = {"N": N, "S": S, "C": C, "accept": acc, "carry": carry, "primal_max": float(ep.max()),
+                   "primal_argmax": int(ep.argmax()), "dual_max": float(ed.max()), "dual_argmax": int(ed.argmax()),
+                   "x": float(xe), "primal_at": {k: float(ep[k - 1]) for k in (10, 50, 100, iters) if k <= iters},
+                   "dual_at": {k: float(ed[k - 1]) for k in (10, 50, 100, iters) if k <= iters},
+                   "primal_last": float(po[-1]), "dual_last": float(do[-1]),
+                   "same_decisions": bool(np.array_equal(np.array(hg["tighten_history"]),
+                                                         np.array(ho["tighten_history"])))}
+            print(json.dumps(row), flush=True)
+            out.append(row)
     return out
 
 
