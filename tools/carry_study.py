@@ -2,7 +2,9 @@
 
 Runs the cfg-1 shape for `iters` outer iterations with carry_residual in {False, 'iteration', 'always'} and prints the
 relative trace error at a few checkpoints, so the growth pattern (roundoff floor vs accumulation) is visible.
-Usage (GPU box):  python tools/carry_study.py [N] [iters]
+Usage (GPU box):  python tools/carry_study.py [N] [iters] [default-only] [diag]
+Any host:         python tools/carry_study.py N iters default-only oracle-only     (writes the cached fp64 oracle run; the
+                  128 / 200 one is committed as tests/golden/cfg1_default_schedule_200.npz)
 """
 import json
 import os
